@@ -1,0 +1,193 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes view of oracle/_ref/libvrt_ref.so -- the UNMODIFIED reference
+CPU implementation (see ref_harness.cpp / ref_harness_scene.cpp / Makefile).  Importable only
+where that library has been built (here: from /root/reference; on the GPU box: the prebuilt file
+that travels with the snapshot).  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_ref.so")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("reference harness not built: run `make -C oracle ref` where /root/reference exists")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vrtref_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().vrtref_last_error().decode())
+
+
+def omp_max_threads():
+    return lib().vrtref_omp_max_threads()
+
+
+_DIR = {np.dtype(np.float32): "f32", np.dtype(np.int16): "i16"}
+
+
+class RefScene:
+    """Reference RaytraceScene<float,float,float> (ior float32) or <ior_t,iorlog_t,diff_t> (ior uint32).
+    image_util.cpp:501-643 (ctor), :645-772 (trace_rays)."""
+
+    def __init__(self, bounds, ior, translucency, loglevel=0):
+        self.bounds = np.asarray(bounds, dtype=np.uint64)
+        self.dim = len(self.bounds)
+        ior = np.ascontiguousarray(ior).reshape(-1)
+        tr = np.ascontiguousarray(translucency, dtype=np.uint32).reshape(-1)
+        self.kind = "f32" if ior.dtype == np.float32 else "u32"
+        if self.kind == "u32":
+            ior = ior.astype(np.uint32, copy=False)
+        self.h = C.c_void_p()
+        fn = getattr(lib(), "vrtref_scene_new_" + self.kind)
+        _check(fn(C.byref(self.h), _p(self.bounds), self.dim, _p(ior), _p(tr), loglevel))
+        db = np.zeros(self.dim, dtype=np.uint64)
+        getattr(lib(), "vrtref_scene_diff_bounds_" + self.kind)(self.h, _p(db))
+        self.diff_bounds = db
+        self.diff_dtype = np.float32 if self.kind == "f32" else np.int16
+        self.dir_dtype = np.float32 if self.kind == "f32" else np.int16
+
+    def close(self):
+        if self.h:
+            getattr(lib(), "vrtref_scene_delete_" + self.kind)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nvox(self):
+        return int(np.prod(self.diff_bounds))
+
+    def interleaved(self):
+        out = np.zeros((self.nvox, self.dim + 1), dtype=self.diff_dtype)
+        getattr(lib(), "vrtref_scene_interleaved_" + self.kind)(self.h, _p(out))
+        return out
+
+    def diff(self, axis):
+        out = np.zeros(self.nvox, dtype=self.diff_dtype)
+        getattr(lib(), "vrtref_scene_diff_" + self.kind)(self.h, axis, _p(out))
+        return out
+
+    def iorlog(self):
+        out = np.zeros(int(np.prod(self.bounds)), dtype=np.float32 if self.kind == "f32" else np.int32)
+        getattr(lib(), "vrtref_scene_iorlog_" + self.kind)(self.h, _p(out))
+        return out
+
+    def translucency_cropped(self):
+        out = np.zeros(self.nvox, dtype=np.uint32)
+        getattr(lib(), "vrtref_scene_translucency_cropped_" + self.kind)(self.h, _p(out))
+        return out
+
+    def trace(self, pos, dir, invscale, min_brightness, iterations, trace_path=False, max_cpu=0):
+        pos = np.ascontiguousarray(pos, dtype=np.uint32).reshape(-1, self.dim)
+        dir = np.ascontiguousarray(dir, dtype=self.dir_dtype).reshape(-1, self.dim)
+        n = pos.shape[0]
+        isc = np.ascontiguousarray(invscale, dtype=np.float32)
+        epos = np.zeros_like(pos); edir = np.zeros_like(dir)
+        eit = np.zeros(n, dtype=np.uint32); light = np.zeros(n, dtype=np.uint32)
+        path = np.zeros((n, iterations, self.dim), dtype=np.uint32) if trace_path else None
+        fn = getattr(lib(), "vrtref_scene_trace_" + self.kind)
+        _check(fn(self.h, C.c_size_t(n), _p(pos), _p(dir), _p(isc), C.c_uint32(min_brightness), C.c_uint32(iterations),
+                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
+        return epos, edir, eit, light, path
+
+
+class RefTracer:
+    """Reference TraceRaysCu<float|diff_t> (cuda_volume_raytracer.h:61-115) on planar gradient arrays."""
+
+    def __init__(self, bounds, diff_planes, translucency_cropped):
+        self.bounds = np.asarray(bounds, dtype=np.uint64)
+        self.dim = len(self.bounds)
+        self.planes = [np.ascontiguousarray(d).reshape(-1) for d in diff_planes]
+        self.kind = _DIR[self.planes[0].dtype]
+        tr = np.ascontiguousarray(translucency_cropped, dtype=np.uint32).reshape(-1)
+        ptrs = (C.c_void_p * self.dim)(*[p.ctypes.data for p in self.planes])
+        self.h = C.c_void_p()
+        _check(getattr(lib(), "vrtref_tracer_new_" + self.kind)(C.byref(self.h), _p(self.bounds), self.dim, ptrs, _p(tr)))
+
+    def close(self):
+        if self.h:
+            getattr(lib(), "vrtref_tracer_delete_" + self.kind)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def interleaved(self):
+        out = np.zeros((int(np.prod(self.bounds)), self.dim + 1), dtype=self.planes[0].dtype)
+        getattr(lib(), "vrtref_tracer_interleaved_" + self.kind)(self.h, _p(out))
+        return out
+
+    def trace(self, pos, dir, invscale, min_brightness, iterations, trace_path=False, max_cpu=0):
+        pos = np.ascontiguousarray(pos, dtype=np.uint32).reshape(-1, self.dim)
+        dir = np.ascontiguousarray(dir).reshape(-1, self.dim)
+        dk = _DIR[dir.dtype]
+        n = pos.shape[0]
+        isc = np.ascontiguousarray(invscale, dtype=np.float32)
+        epos = np.zeros_like(pos); edir = np.zeros_like(dir)
+        eit = np.zeros(n, dtype=np.uint32); light = np.zeros(n, dtype=np.uint32)
+        path = np.zeros((n, iterations, self.dim), dtype=np.uint32) if trace_path else None
+        fn = getattr(lib(), "vrtref_tracer_trace_%s_%s" % (self.kind, dk))
+        _check(fn(self.h, C.c_size_t(n), _p(pos), _p(dir), _p(isc), C.c_uint32(min_brightness), C.c_uint32(iterations),
+                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
+        return epos, edir, eit, light, path
+
+
+def trace_live(volume, translucency, bounds, invscale, pos, dir, iterations, min_brightness, trace_path=False, threads=0):
+    """Reference trace_rays_cpu (cu:376-394) instantiated with a LIVE translucency plane and brightness_t
+    (cu:337-341); `volume` is the interleaved [d..,extra] array of the scene's DiffType."""
+    bounds = np.asarray(bounds, dtype=np.uint64)
+    dim = len(bounds)
+    volume = np.ascontiguousarray(volume)
+    vk = _DIR[volume.dtype]
+    tr = np.ascontiguousarray(translucency, dtype=np.uint32).reshape(-1)
+    pos = np.ascontiguousarray(pos, dtype=np.uint32).reshape(-1, dim)
+    dir = np.ascontiguousarray(dir).reshape(-1, dim)
+    dk = _DIR[dir.dtype]
+    n = pos.shape[0]
+    isc = np.ascontiguousarray(invscale, dtype=np.float32)
+    epos = np.zeros_like(pos); edir = np.zeros_like(dir)
+    eit = np.zeros(n, dtype=np.uint32); light = np.zeros(n, dtype=np.uint32)
+    path = np.zeros((n, iterations, dim), dtype=np.uint32) if trace_path else None
+    if threads <= 0:
+        threads = omp_max_threads()
+    fn = getattr(lib(), "vrtref_trace_live_%s_%s" % (vk, dk))
+    _check(fn(_p(volume), _p(tr), _p(bounds), dim, _p(isc), C.c_size_t(n), _p(pos), _p(dir), C.c_uint32(iterations),
+              C.c_uint32(min_brightness), int(trace_path), int(threads), _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
+    return epos, edir, eit, light, path
+
+
+def interpolate(img, bounds, pos):
+    """Reference host interpolator<T> (image_util.h:348-431)."""
+    bounds = np.asarray(bounds, dtype=np.uint64)
+    dim = len(bounds)
+    img = np.ascontiguousarray(img).reshape(-1)
+    pos = np.ascontiguousarray(pos, dtype=np.uint32).reshape(-1, dim)
+    kind = {np.dtype(np.float32): "f32", np.dtype(np.uint32): "u32", np.dtype(np.int32): "i32"}[img.dtype]
+    out = np.zeros(pos.shape[0], dtype=img.dtype)
+    _check(getattr(lib(), "vrtref_interpolate_" + kind)(_p(img), _p(bounds), dim, _p(pos), C.c_size_t(pos.shape[0]), _p(out)))
+    return out

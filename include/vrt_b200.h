@@ -1,0 +1,148 @@
+/* vrt_b200.h -- C ABI of the B200-native volume ray marcher.
+ *
+ * This is the drop-in boundary underneath the reference's C++ class TraceRaysCu<DiffType>
+ * (reference: src/cuda_volume_raytracer.h:61-115).  Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point cites the reference interface it replaces ("ref:" paths are relative to the
+ * reference's src/ directory; "cu:" = cuda_volume_raytracer.cu).  INTEGRATION.md shows the bindings a
+ * reference maintainer adds on top (the TraceRaysCu<> shim, ctypes, JNI).
+ *
+ * Data contract (ref: types.h:5-11, cu:103-113):
+ *   positions   uint32 16.16 fixed point, `dim` per ray, packed [ray][axis]; CROPPED-volume coordinates
+ *               (API coordinate - 0x10000, the caller shifts: image_util.cpp:692,710,770-771)
+ *   directions  float32, or int16 with unit 0x100 (dir_t), packed [ray][axis], already multiplied by n(start)
+ *   volume      gradient field, `dim`+1 channels per voxel {d0,..,d(dim-1),extra}, float32 or int16 (diff_t),
+ *               axis 0 slowest; extra = (0x7FFFFFFF - translucency)/0x10000 (cu:654-659); a ray stops where the
+ *               interpolated extra channel is > 0 (cu:343)
+ *   translucency uint32 per voxel of the cropped volume (0xFFFFFFFF = clear)
+ *
+ * All functions return VRT_OK (0) or a VRT_ERR_* code; vrt_last_error() gives the message of the calling
+ * thread's last failure.  There is no CPU fallback: without a CUDA device every compute call fails.
+ * A scene is immutable after creation; concurrent vrt_trace calls on one scene from several host threads
+ * are allowed (ref boundary contract: the JNI binding can be entered from any Java thread).
+ */
+#ifndef VRT_B200_H
+#define VRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VRT_API __attribute__((visibility("default")))
+#else
+#define VRT_API
+#endif
+
+typedef struct vrt_scene vrt_scene; /* opaque; owns the device copy of the volume */
+
+enum { VRT_OK = 0, VRT_ERR_INVALID = 1, VRT_ERR_CUDA = 2, VRT_ERR_NOMEM = 3, VRT_ERR_UNSUPPORTED = 4 };
+
+/* element types */
+enum { VRT_F32 = 0, VRT_I16 = 1, VRT_U32 = 2 };
+
+/* vrt_trace flags */
+enum {
+    VRT_TRACE_DEFAULT           = 0,
+    /* attenuate by the translucency plane every step and stop below min_brightness (the template code at
+     * cu:337-341,370-373, which the reference's shipped call sites compile out: cu:853,859,...).  Without this
+     * flag remaining_light is 0xFFFFFFFF for every ray and min_brightness is ignored, exactly as shipped (cu:785). */
+    VRT_TRACE_LIVE_TRANSLUCENCY = 1u << 0,
+    /* write the per-step polyline (ref trace_paths; cu:333,348,352-358): path[ray][iterations][dim], REVERSE order */
+    VRT_TRACE_PATHS             = 1u << 1
+};
+
+/* vrt_scene_create* flags */
+enum {
+    VRT_SCENE_DEFAULT = 0,
+    VRT_SCENE_BORROW  = 1u << 0  /* vrt_scene_create_device: use the caller's device buffers in place (no copy, not freed) */
+};
+
+/* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */
+enum {
+    VRT_OPT_KERNEL        = 0,  /* 0 auto, 1 reference-like (reload every step), 2 register cell cache, 3 cell cache + packed f32x2 */
+    VRT_OPT_BLOCK_THREADS = 1,  /* 64..512, multiple of 32 */
+    VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
+    VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
+    VRT_OPT_STEPS_PER_POLL= 4   /* marching steps between two refill polls */
+};
+
+VRT_API const char *vrt_last_error(void);
+VRT_API const char *vrt_version(void);
+
+/* ref: init() cu:82-101 (device count, cached in the global `inited`). */
+VRT_API int vrt_device_count(int *count);
+
+/* ref: TraceRaysCu<DiffType>::TraceRaysCu(bounds, diff[dim] planar, translucency_cropped)  cuda_volume_raytracer.h:74-82,
+ * cu:637-720: builds the extra channel, interleaves, uploads.  Host pointers.  dim is 2 or 3; bounds[d] <= 65535 and
+ * prod(bounds) < 2^32 (the reference indexes in uint16/uint32: cu:113,321). */
+VRT_API int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                             const void *const *diff_planes, const uint32_t *translucency_cropped, unsigned flags);
+
+/* Same, from an already interleaved HOST volume [nvox][dim+1] (the layout the ctor produces, cu:660-669). */
+VRT_API int vrt_scene_create_interleaved(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                                         const void *volume_interleaved, const uint32_t *translucency_cropped, unsigned flags);
+
+/* Same, from DEVICE memory on `device` (e.g. the buffer an NCCL broadcast just filled: the B200 replacement for the
+ * per-device host upload at cu:676-686).  With VRT_SCENE_BORROW the buffers are used in place. */
+VRT_API int vrt_scene_create_device(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                                    const void *d_volume_interleaved, const uint32_t *d_translucency_cropped, unsigned flags);
+
+/* Scene prep on the GPU ("next" row f1; ref: RaytraceScene ctor image_util.cpp:501-643 = crop translucency,
+ * log(n)*0x420000, 3x3x3 {14,47,162} stencil / (812*256), then the TraceRaysCu ctor).  ior is float32 (float scene) or
+ * uint32 16.16 (int16 scene) over the UNCROPPED bounds; the scene's bounds are bounds-2.  ior/translucency are host
+ * pointers unless ptrs_on_device != 0. */
+VRT_API int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64_t *bounds, int ior_dtype,
+                                      const void *ior, const uint32_t *translucency, int ptrs_on_device, unsigned flags);
+
+/* ref: TraceRaysCu<DiffType>::~TraceRaysCu cu:974-989. */
+VRT_API int vrt_scene_destroy(vrt_scene *scene);
+
+/* Introspection: ref public member TraceRaysCu::_output_sizes (cuda_volume_raytracer.h:73) and the device buffers
+ * (so that a multi-GPU caller can broadcast into them).  Any out pointer may be NULL. */
+VRT_API int vrt_scene_info(const vrt_scene *scene, int *device, int *dim, uint64_t *bounds, int *diff_dtype,
+                           void **d_volume_interleaved, uint32_t **d_translucency, uint64_t *volume_bytes);
+/* Copy the staged volume back to the host (the reference keeps such a host copy itself: _diff_interleaved,
+ * cuda_volume_raytracer.h:67).  host_volume: volume_bytes; host_translucency: nvox uint32; either may be NULL. */
+VRT_API int vrt_scene_download(const vrt_scene *scene, void *host_volume, uint32_t *host_translucency);
+VRT_API int vrt_scene_set_option(vrt_scene *scene, int key, int64_t value);
+VRT_API int vrt_scene_get_option(const vrt_scene *scene, int key, int64_t *value);
+
+/* ref: TraceRaysCu<DiffType>::trace_rays_cu<DirType>(start_position, start_direction, end_position&, end_direction&,
+ * end_iteration&, remaining_light&, path&, scale_vec, minimum_brightness, iterations, trace_paths, Options)
+ * cuda_volume_raytracer.h:84-97, cu:722-972.  HOST buffers; blocking.  Outputs are caller-allocated:
+ * end_pos n*dim u32, end_dir n*dim (dir_dtype), end_iter n u32, remaining_light n u32, path n*iterations*dim u32
+ * (only with VRT_TRACE_PATHS, else may be NULL).  In-place (end_* == start_*) is allowed (the JNI binding does that:
+ * java_binding.cpp:158-160).  end_iter follows cu:953-956: k+1 if the ray left the volume after k steps, k if it was
+ * stopped in step k (opaque / below min_brightness), `iterations` if the cap was hit. */
+VRT_API int vrt_trace(vrt_scene *scene, uint64_t n_rays, const uint32_t *start_pos, const void *start_dir, int dir_dtype,
+                      const float *invscale, uint32_t min_brightness, uint32_t iterations, unsigned flags,
+                      uint32_t *end_pos, void *end_dir, uint32_t *end_iter, uint32_t *remaining_light, uint32_t *path);
+
+/* Same with DEVICE buffers on the scene's device, enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream);
+ * returns without synchronising.  This is the call bench.py times for the HBM-resident figure. */
+VRT_API int vrt_trace_device(vrt_scene *scene, uint64_t n_rays, const uint32_t *d_start_pos, const void *d_start_dir,
+                             int dir_dtype, const float *invscale, uint32_t min_brightness, uint32_t iterations,
+                             unsigned flags, uint32_t *d_end_pos, void *d_end_dir, uint32_t *d_end_iter,
+                             uint32_t *d_remaining_light, uint32_t *d_path, void *cuda_stream);
+
+/* Ray pre-processing on the GPU ("next" row f2; ref: RaytraceScene::trace_rays image_util.cpp:675-719): range check
+ * against the UNCROPPED bounds, pos -= 0x8000, n = trilinear(ior, pos), dir *= n, pos -= 0x8000.  Device buffers, in
+ * place.  *first_bad_ray receives 1 + index of the first out-of-range ray (0 if none; the reference throws there).
+ * Needs a scene made by vrt_scene_create_from_ior (which keeps ior on the device). */
+VRT_API int vrt_normalise_rays_device(vrt_scene *scene, uint64_t n_rays, uint32_t *d_pos, void *d_dir, int dir_dtype,
+                                      int64_t *first_bad_ray, void *cuda_stream);
+
+/* Measurement helper for the roofline denominator that MEASURED_PEAKS.json does not hold:
+ * random 32-byte-sector gather over a `bytes`-sized device buffer (L2 resident when bytes << L2 size), returns GB/s. */
+VRT_API int vrt_measure_gather_bandwidth(int device, uint64_t bytes, int sector_bytes, int iters, double *gb_per_s);
+
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+VRT_API uint64_t vrt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRT_B200_H */

@@ -9,31 +9,34 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_ref.so")
+# the same harness compiled by nvcc for sm_100: TraceRaysCu<> then runs the reference's own CUDA kernel
+# (trace_rays_gpu, cu:397-414) for more than 0x80 rays -- the GPU-side comparator on the B200 box
+CUDA_LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_ref_cuda.so")
 
-_lib = None
+_libs = {}
 
 
-def available():
-    return os.path.exists(LIB_PATH)
+def available(cuda=False):
+    return os.path.exists(CUDA_LIB_PATH if cuda else LIB_PATH)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            raise RuntimeError("reference harness not built: run `make -C oracle ref` where /root/reference exists")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.vrtref_last_error.restype = C.c_char_p
-    return _lib
+def lib(cuda=False):
+    if cuda not in _libs:
+        if not available(cuda):
+            raise RuntimeError("reference harness not built: run `make -C oracle ref ref_cuda` where /root/reference exists")
+        l = C.CDLL(CUDA_LIB_PATH if cuda else LIB_PATH)
+        l.vrtref_last_error.restype = C.c_char_p
+        _libs[cuda] = l
+    return _libs[cuda]
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def _check(rc):
+def _check(rc, cuda=False):
     if rc != 0:
-        raise RuntimeError(lib().vrtref_last_error().decode())
+        raise RuntimeError(lib(cuda).vrtref_last_error().decode())
 
 
 def omp_max_threads():
@@ -116,7 +119,8 @@ class RefScene:
 class RefTracer:
     """Reference TraceRaysCu<float|diff_t> (cuda_volume_raytracer.h:61-115) on planar gradient arrays."""
 
-    def __init__(self, bounds, diff_planes, translucency_cropped):
+    def __init__(self, bounds, diff_planes, translucency_cropped, cuda=False):
+        self.cuda = cuda
         self.bounds = np.asarray(bounds, dtype=np.uint64)
         self.dim = len(self.bounds)
         self.planes = [np.ascontiguousarray(d).reshape(-1) for d in diff_planes]
@@ -124,11 +128,11 @@ class RefTracer:
         tr = np.ascontiguousarray(translucency_cropped, dtype=np.uint32).reshape(-1)
         ptrs = (C.c_void_p * self.dim)(*[p.ctypes.data for p in self.planes])
         self.h = C.c_void_p()
-        _check(getattr(lib(), "vrtref_tracer_new_" + self.kind)(C.byref(self.h), _p(self.bounds), self.dim, ptrs, _p(tr)))
+        _check(getattr(lib(cuda), "vrtref_tracer_new_" + self.kind)(C.byref(self.h), _p(self.bounds), self.dim, ptrs, _p(tr)), cuda)
 
     def close(self):
         if self.h:
-            getattr(lib(), "vrtref_tracer_delete_" + self.kind)(self.h)
+            getattr(lib(self.cuda), "vrtref_tracer_delete_" + self.kind)(self.h)
             self.h = None
 
     def __del__(self):
@@ -151,9 +155,9 @@ class RefTracer:
         epos = np.zeros_like(pos); edir = np.zeros_like(dir)
         eit = np.zeros(n, dtype=np.uint32); light = np.zeros(n, dtype=np.uint32)
         path = np.zeros((n, iterations, self.dim), dtype=np.uint32) if trace_path else None
-        fn = getattr(lib(), "vrtref_tracer_trace_%s_%s" % (self.kind, dk))
+        fn = getattr(lib(self.cuda), "vrtref_tracer_trace_%s_%s" % (self.kind, dk))
         _check(fn(self.h, C.c_size_t(n), _p(pos), _p(dir), _p(isc), C.c_uint32(min_brightness), C.c_uint32(iterations),
-                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
+                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)), self.cuda)
         return epos, edir, eit, light, path
 
 

@@ -19,7 +19,9 @@
 // TU 1 of 2: includes the reference .cu (TraceRaysCu<> + trace_rays_cpu<>).  The scene-level wrappers
 // live in ref_harness_scene.cpp because tuple_io.h and io_util.h both declare `print`.
 
+#ifndef VRTREF_CUDA      // VRTREF_CUDA: the same harness compiled by nvcc for sm_100 = the reference's own CUDA trace
 #define NCUDA 1
+#endif
 #include "cuda_volume_raytracer.cu"   // found via -I$(REF_SRC)
 
 #include <cstring>
@@ -128,14 +130,24 @@ extern "C" {
 
 const char *vrtref_last_error() { return g_err.c_str(); }
 int vrtref_omp_max_threads() { return omp_get_max_threads(); }
+int vrtref_is_cuda_build()
+{
+#ifdef VRTREF_CUDA
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 // ---- TraceRaysCu<> (boundary level, h:61-115) ----
 int vrtref_tracer_new_f32(void **out, const size_t *bounds, int dim, const float *const *diff, const uint32_t *tr) { return tracer_new<float>(out, bounds, dim, diff, tr); }
 int vrtref_tracer_new_i16(void **out, const size_t *bounds, int dim, const int16_t *const *diff, const uint32_t *tr) { return tracer_new<diff_t>(out, bounds, dim, diff, tr); }
 void vrtref_tracer_delete_f32(void *h) { delete static_cast<TracerBox<float>*>(h); }
 void vrtref_tracer_delete_i16(void *h) { delete static_cast<TracerBox<diff_t>*>(h); }
+#ifndef VRTREF_CUDA   // private member access needs -fno-access-control (host build only)
 void vrtref_tracer_interleaved_f32(void *h, float *out)   { auto *b = static_cast<TracerBox<float>*>(h);  size_t n = b->diff[0].size() * (b->diff.size() + 1); std::memcpy(out, b->tracer->_diff_interleaved.get(), n * sizeof(float)); }
 void vrtref_tracer_interleaved_i16(void *h, int16_t *out) { auto *b = static_cast<TracerBox<diff_t>*>(h); size_t n = b->diff[0].size() * (b->diff.size() + 1); std::memcpy(out, b->tracer->_diff_interleaved.get(), n * sizeof(int16_t)); }
+#endif
 
 #define VRTREF_TRACER_TRACE(NAME, DIFF, DIR)                                                                                     \
 int NAME(void *h, size_t n, const uint32_t *pos, const DIR *dir, const float *invscale, uint32_t minb, uint32_t iterations,      \

@@ -1,0 +1,303 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libvrt_b200.so), against
+  (a) the CPU oracle in ROUND_DEVICE mode -- bit-exact (positions, directions, step counts, light, paths),
+  (b) the reference's own CUDA kernel compiled for sm_100 (oracle/_ref/libvrt_ref_cuda.so) -- bit-exact,
+  (c) the reference's CPU build through the oracle's ROUND_HOST mode -- within the north_star tolerance
+      (1e-3 voxel, 1e-5 rad on smooth fields).
+Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from tests import scenes as S
+
+pytestmark = pytest.mark.gpu
+EQ = np.array_equal
+
+KERNELS = [1, 2, 3]
+REFILLS = [0, 1, 16, 32]
+
+
+@pytest.fixture(scope="module")
+def vrt():
+    import volumeraytracer_b200 as v
+    v.lib()
+    return v
+
+
+def _mk(vrt, oracle, shape, seed, volk, opaque=0.01, absorb=False):
+    ior, tr = S.random_scene(shape, seed=seed, kind="f32" if volk == "f32" else "u32", opaque_fraction=opaque)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    if absorb:
+        trc = trc.copy()
+        trc[trc != 0] -= np.uint32(1 << 24)
+    vol = oracle.fold(planes, trc)
+    tracer = vrt.TraceRaysCu(ob, planes, trc)
+    return ob, planes, trc, vol, tracer
+
+
+def _assert_same(got, want, what=""):
+    names = ["end_position", "end_direction", "end_iteration", "remaining_light", "path"]
+    for g, w, nme in zip(got, want, names):
+        if w is None:
+            continue
+        assert EQ(g, w), "%s %s differs (%d of %d)" % (what, nme, int(np.sum(g != w)), g.size)
+
+
+@pytest.mark.parametrize("kind", ["u32", "f32"])
+def test_scaling_test_known_answer(vrt, oracle, kind):
+    """The reference's scaling_test (cuda_volume_raytracer_test.h:4-75) through the boundary class."""
+    inp = S.scaling_test_inputs(kind)
+    ob, iorlog, planes, trc = oracle.prep(inp["bounds"], inp["ior"], inp["translucency"])
+    vol = oracle.fold(planes, trc)
+    p2, d2 = oracle.normalise(inp["bounds"], inp["ior"], inp["pos"], inp["dir"])
+    want = oracle.trace(vol, ob, p2, d2, inp["invscale"], inp["iterations"], trace_path=True, round_mode=oracle.ROUND_DEVICE)
+    t = vrt.TraceRaysCu(ob, planes, trc)
+    got = t.trace_rays_cu(p2, d2, inp["invscale"], 0, inp["iterations"], trace_paths=True)
+    _assert_same(got, want, "scaling_test")
+    # the reference's own assertions: step count 46718 +- 100 and |T| = n at the exit (cuda_volume_raytracer_test.h:48-52)
+    assert abs(int(got[2][0]) - 46718) <= 100 and abs(int(got[2][1]) - 46718) <= 100
+    unit = 1.0 if kind == "f32" else 256.0
+    ratio = got[1][:, 0].astype(np.float64) / inp["dir"][:, 0].astype(np.float64)
+    n_end = oracle.interp(inp["ior"], inp["bounds"], got[0] + np.uint32(0x10000)).astype(np.float64) / (1.0 if kind == "f32" else 65536.0)
+    assert np.all(np.abs(ratio - n_end) <= 1e-5 + (0 if kind == "f32" else 1.0 / 256) + 2e-3), (ratio, n_end, unit)
+    # and against the reference CPU's known answers: same step counts, positions within 1e-3 voxel
+    known = S.SCALING_KNOWN[kind]
+    assert got[2].tolist() == known["eit"]
+    assert np.abs(got[0].ravel().astype(np.int64) + 0x10000 - np.array(known["epos"], dtype=np.int64)).max() <= 66
+
+
+@pytest.mark.parametrize("kver", KERNELS)
+@pytest.mark.parametrize("refill", REFILLS)
+def test_kernel_variants_bit_exact(vrt, oracle, kver, refill):
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (40, 36, 44), 5, "f32")
+    pos, d = S.random_rays(ob, 20000, seed=77)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 0.9, 1.1], 600, round_mode=oracle.ROUND_DEVICE)
+    t.set_option(vrt.VRT_OPT_KERNEL, kver)
+    t.set_option(vrt.VRT_OPT_REFILL, refill)
+    for block in (64, 128, 256):
+        t.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)
+        got = t.trace_rays_cu(pos, d, [1.0, 0.9, 1.1], 0, 600)
+        _assert_same(got, want, "kver=%d refill=%d block=%d" % (kver, refill, block))
+    assert len(np.unique(want[2])) > 20
+
+
+@pytest.mark.parametrize("volk", ["f32", "i16"])
+@pytest.mark.parametrize("dirk", ["f32", "i16"])
+@pytest.mark.parametrize("live", [False, True])
+def test_all_type_combinations_and_paths(vrt, oracle, volk, dirk, live):
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (30, 34, 28), 9, volk, opaque=0.004, absorb=live)
+    pos, d = S.random_rays(ob, 5000, seed=3, dir_kind=dirk, scale=1.2)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    isc = [1.0, 1.25, 0.8]
+    minb = 0x40000000
+    want = oracle.trace(vol, ob, pos, d, isc, 300, translucency=trc if live else None, min_brightness=minb, trace_path=True,
+                        round_mode=oracle.ROUND_DEVICE)
+    got = t.trace_rays_cu(pos, d, isc, minb, 300, trace_paths=True, live_translucency=live)
+    _assert_same(got, want, "paths")
+    for kver in KERNELS:
+        t.set_option(vrt.VRT_OPT_KERNEL, kver)
+        got = t.trace_rays_cu(pos, d, isc, minb, 300, live_translucency=live)
+        _assert_same(got, want[:4], "kver %d" % kver)
+    if live:
+        assert np.any(got[3] < minb) and np.any(got[3] == 0xFFFFFFFF)
+    else:
+        assert np.all(got[3] == 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("volk", ["f32", "i16"])
+@pytest.mark.parametrize("dirk", ["f32", "i16"])
+@pytest.mark.parametrize("live", [False, True])
+def test_two_dimensional(vrt, oracle, volk, dirk, live):
+    """dim == 2 (f4), including the reference's second-x-lerp quirk (cu:207-208)."""
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (60, 47), 13, volk, opaque=0.004, absorb=live)
+    pos, d = S.random_rays(ob, 4000, seed=8, dir_kind=dirk, scale=1.1)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.1], 250, translucency=trc if live else None, min_brightness=0x40000000,
+                        trace_path=True, round_mode=oracle.ROUND_DEVICE)
+    got = t.trace_rays_cu(pos, d, [1.0, 1.1], 0x40000000, 250, trace_paths=True, live_translucency=live)
+    _assert_same(got, want, "2-D")
+
+
+def test_edge_cases(vrt, oracle):
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (20, 22, 24), 1, "f32")
+    # empty batch
+    out = t.trace_rays_cu(np.zeros((0, 3), np.uint32), np.zeros((0, 3), np.float32), [1, 1, 1], 0, 100)
+    assert out[0].shape == (0, 3) and out[2].shape == (0,)
+    # ragged sizes: 1, 31, 33, 129 rays; rays starting out of bounds (report 1 step), zero direction (NaN step),
+    # iterations == 1 (cap immediately), negative-going rays that wrap below zero
+    for n in (1, 31, 33, 129):
+        pos, d = S.random_rays(ob, n, seed=n)
+        pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+        pos[0] = [0xFFFF0000, 0x20000, 0x20000]
+        if n > 2:
+            d[1] = 0.0
+            d[2] = [-1.0, 0.0, 0.0]
+            pos[2] = [0x1000, 0x28000, 0x28000]
+        for its in (1, 2, 50):
+            want = oracle.trace(vol, ob, pos, d, [1, 1, 1], its, round_mode=oracle.ROUND_DEVICE)
+            got = t.trace_rays_cu(pos, d, [1, 1, 1], 0, its)
+            _assert_same(got, want, "n=%d its=%d" % (n, its))
+            assert got[2][0] == 1
+    # argument errors are reported, not crashed on
+    with pytest.raises(vrt.VrtError):
+        t.trace_rays_cu(np.zeros(5, np.uint32), np.zeros(5, np.float32), [1, 1, 1], 0, 10)
+    with pytest.raises(vrt.VrtError):
+        vrt.TraceRaysCu([4, 4, 4, 4], [np.zeros(256, np.float32)] * 4, np.zeros(256, np.uint32))
+
+
+def test_host_call_chunking_and_in_place(vrt, oracle):
+    """vrt_trace pipelines chunks over two streams and writes results back in place on the device."""
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (36, 30, 33), 4, "f32")
+    pos, d = S.random_rays(ob, 30011, seed=12)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1, 1, 1], 400, round_mode=oracle.ROUND_DEVICE)
+    for chunk in (0, 1000, 4096, 30011):
+        t.set_option(vrt.VRT_OPT_CHUNK_RAYS, chunk)
+        got = t.trace_rays_cu(pos, d, [1, 1, 1], 0, 400)
+        _assert_same(got, want, "chunk %d" % chunk)
+
+
+def test_gpu_scene_prep_and_api_level(vrt, oracle):
+    """f1 + f2 on the GPU: RaytraceScene (prep, normalise, march, coordinate shifts) vs the oracle's restatement."""
+    import torch
+    for kind, dirk, shape in (("f32", "f32", (26, 30, 22)), ("u32", "i16", (26, 30, 22)), ("f32", "f32", (40, 33)), ("u32", "i16", (40, 33))):
+        ior, tr = S.random_scene(shape, seed=31, kind=kind, opaque_fraction=0.01)
+        ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+        vol = oracle.fold(planes, trc)
+        sc = vrt.RaytraceScene(shape, ior, tr)
+        co = sc._calculation_object
+        assert co._output_sizes == list(ob)
+        host, host_tr = co.download_volume()
+        assert EQ(host_tr, trc)
+        mism = np.sum(host.reshape(vol.shape) != vol)
+        assert mism <= max(1, vol.size // 1000000), "GPU scene prep differs from the oracle in %d of %d values" % (mism, vol.size)
+        pos, d = S.random_rays(shape, 3000, seed=6, dir_kind=dirk)
+        isc = [1.0, 0.75, 1.5][:len(shape)]
+        p2, d2 = oracle.normalise(shape, ior, pos, d)
+        want = oracle.trace(host.reshape(vol.shape), ob, p2, d2, isc, 300, trace_path=True, round_mode=oracle.ROUND_DEVICE)
+        got = sc.trace_rays(pos, d, isc, 0, 300, trace_path=True)
+        assert EQ(got[0], want[0] + np.uint32(0x10000))
+        assert EQ(got[1], want[1]) and EQ(got[2], want[2]) and EQ(got[3], want[3])
+        assert EQ(got[4], want[4] + np.uint32(0x10000))
+        # out-of-range start is an error, as in the reference (image_util.cpp:686-691)
+        bad = pos.copy(); bad[5, 0] = 0x8000
+        with pytest.raises(vrt.VrtError):
+            sc.trace_rays(bad, d, isc, 0, 10)
+        sc.close()
+
+
+def test_against_reference_cuda_kernel(vrt, oracle):
+    """Bit-exact against the reference's OWN CUDA kernel (trace_rays_gpu, cu:397-414) compiled for sm_100."""
+    from oracle import ref
+    if not ref.available(cuda=True):
+        pytest.skip("oracle/_ref/libvrt_ref_cuda.so not built")
+    for volk, dirk in (("f32", "f32"), ("i16", "i16"), ("f32", "i16"), ("i16", "f32")):
+        ob, planes, trc, vol, t = _mk(vrt, oracle, (34, 30, 38), 17, volk)
+        pos, d = S.random_rays(ob, 9000, seed=23, dir_kind=dirk)
+        pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+        rt = ref.RefTracer(ob, planes, trc, cuda=True)
+        want = rt.trace(pos, d, [1, 1, 1], 0, 500)
+        got = t.trace_rays_cu(pos, d, [1, 1, 1], 0, 500)
+        _assert_same(got, want[:4], "vs reference CUDA %s/%s" % (volk, dirk))
+        rt.close()
+
+
+def test_within_tolerance_of_reference_cpu_on_smooth_field(vrt, oracle):
+    """north_star tolerance vs the reference's CPU trace (ROUND_HOST = bit-exact restatement of it): end positions
+    within 1e-3 voxel, directions within 1e-5 rad, identical termination step counts, on a smooth analytic field."""
+    from volumeraytracer_b200 import workloads as W
+    size = 64
+    ior = W.ior_sines(size, base=1.3, amp=0.05, period=48.0)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    ob, iorlog, planes, trc = oracle.prep(ior.shape, ior, tr)
+    vol = oracle.fold(planes, trc)
+    t = vrt.TraceRaysCu(ob, planes, trc)
+    pos, d = W.rays_parallel_x(96, 96, 3.0, size - 4.0, x0=2.0)
+    pos, d = oracle.normalise(ior.shape, ior, pos, d)
+    cpu = oracle.trace(vol, ob, pos, d, [1, 1, 1], 1024, round_mode=oracle.ROUND_HOST)
+    got = t.trace_rays_cu(pos, d, [1, 1, 1], 0, 1024)
+    assert EQ(got[2], cpu[2]), "termination step counts differ on %d rays" % int(np.sum(got[2] != cpu[2]))
+    dp = np.abs(got[0].astype(np.int64) - cpu[0].astype(np.int64)).max() / 65536.0
+    assert dp <= 1e-3, dp
+    a, b = got[1].astype(np.float64), cpu[1].astype(np.float64)
+    cosang = np.sum(a * b, axis=1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+    ang = np.arccos(np.clip(cosang, -1, 1))
+    assert ang.max() <= 1e-5, ang.max()
+
+
+def test_config1_constant_index(vrt, oracle):
+    """BASELINE config 1: 64^3 constant-index volume, 4096 straight rays -- directions unchanged bit-exactly, y/z
+    unchanged, all rays the same step count, remaining_light 0xFFFFFFFF; float and int16 variants."""
+    from volumeraytracer_b200 import workloads as W
+    size = 64
+    for kind in ("f32", "u32"):
+        ior = W.ior_constant(size, 1.0)
+        if kind == "u32":
+            ior = W.ior_to_u32(ior)
+        tr = np.full((size,) * 3, 0xFFFFFFFF, np.uint32)
+        pos, d = W.rays_parallel_x(64, 64, 1.5, 62.5, x0=1.5)
+        if kind == "u32":
+            d = W.dirs_to_i16(d)
+        sc = vrt.RaytraceScene((size,) * 3, ior, tr)
+        epos, edir, eit, light, _ = sc.trace_rays(pos, d, [1, 1, 1], 0, 1024)
+        assert EQ(edir, d), "directions must be unchanged in a constant-index volume"
+        assert EQ(epos[:, 1:], pos[:, 1:])
+        assert len(np.unique(eit)) == 1 and 200 < int(eit[0]) < 280
+        assert np.all(light == 0xFFFFFFFF)
+        ob, iorlog, planes, trc = oracle.prep((size,) * 3, ior, tr)
+        p2, d2 = oracle.normalise((size,) * 3, ior, pos, d)
+        want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 1024, round_mode=oracle.ROUND_DEVICE)
+        assert EQ(epos, want[0] + np.uint32(0x10000)) and EQ(eit, want[2])
+        sc.close()
+
+
+def test_size_independent_properties_large(vrt, oracle):
+    """At a size the CPU oracle cannot cover in seconds: (i) all kernel variants and refill policies agree bit for bit
+    (2M rays, 256^3 Luneburg lens = BASELINE config 2 geometry), (ii) a 1/64 subsample matches the oracle exactly,
+    (iii) tracing in two halves equals tracing at once (ray independence), (iv) permuting the rays permutes the output."""
+    from volumeraytracer_b200 import workloads as W
+    size = 256
+    ior = W.ior_luneburg(size, 100.0)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    sc = vrt.RaytraceScene(ior.shape, ior, tr)
+    co = sc._calculation_object
+    pos, d = W.rays_parallel_x(1024, 1024, 30.0, 225.0, x0=2.0)
+    # normalise on the host oracle for the subsample, on the GPU for everything
+    import torch
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).cuda(); tdir = torch.from_numpy(d.reshape(-1)).cuda()
+    co.normalise_rays_device(tpos, tdir)
+    results = []
+    for kver, refill in ((1, 0), (2, 16), (3, 1), (3, 32)):
+        co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_REFILL, refill)
+        out = co.trace_device(tpos, tdir, [1, 1, 1], 0, 4096)
+        torch.cuda.synchronize()
+        results.append([o.cpu().numpy() for o in out])
+    for r in results[1:]:
+        for a, b in zip(results[0], r):
+            assert EQ(a, b)
+    base = results[0]
+    n = pos.shape[0]
+    # (ii) subsample vs oracle (volume read back from the device so both sides consume identical bits)
+    sel = np.arange(0, n, 64)
+    host_vol, _ = co.download_volume()
+    p_h = tpos.cpu().numpy().view(np.uint32).reshape(-1, 3)[sel]; d_h = tdir.cpu().numpy().reshape(-1, 3)[sel]
+    want = oracle.trace(host_vol, co._output_sizes, p_h, d_h, [1, 1, 1], 4096, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(base[0].view(np.uint32).reshape(-1, 3)[sel], want[0])
+    assert EQ(base[1].reshape(-1, 3)[sel], want[1])
+    assert EQ(base[2].view(np.uint32)[sel], want[2])
+    # physics sanity of config 2: rays through the lens converge near the far focus (x ~ 227.5, y = z = 127.5)
+    # (iii) halves
+    h = n // 2
+    o1 = co.trace_device(tpos[:h * 3].clone(), tdir[:h * 3].clone(), [1, 1, 1], 0, 4096)
+    o2 = co.trace_device(tpos[h * 3:].clone(), tdir[h * 3:].clone(), [1, 1, 1], 0, 4096)
+    torch.cuda.synchronize()
+    assert EQ(np.concatenate([o1[0].cpu().numpy(), o2[0].cpu().numpy()]), base[0])
+    assert EQ(np.concatenate([o1[2].cpu().numpy(), o2[2].cpu().numpy()]), base[2])
+    # (iv) permutation
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    pp = tpos.view(-1, 3)[perm].contiguous().view(-1); dd = tdir.view(-1, 3)[perm].contiguous().view(-1)
+    op = co.trace_device(pp, dd, [1, 1, 1], 0, 4096)
+    torch.cuda.synchronize()
+    assert EQ(op[0].view(-1, 3).cpu().numpy(), base[0].reshape(-1, 3)[perm.cpu().numpy()])
+    assert EQ(op[2].cpu().numpy(), base[2][perm.cpu().numpy()])
+    sc.close()

@@ -123,8 +123,9 @@ def test_device_vs_host_rounding_within_tolerance(oracle):
     """ROUND_DEVICE (cvt.rni, the reference's CUDA build) and ROUND_HOST (std::round, its CPU build) differ only
     on exact .5 ties: on a smooth field end positions agree to << 1e-3 voxel and step counts are identical."""
     shape = (48, 40, 44)
-    ior, tr = S.random_scene(shape, seed=2, kind="f32", opaque_fraction=0.0)
-    tr[:] = 0xFFFFFFFF
+    from volumeraytracer_b200 import workloads as W
+    ior = W.ior_random_smooth(shape, 2, lo=1.0, hi=1.1)       # smooth field (north_star: "on smooth fields")
+    tr = np.full(shape, 0xFFFFFFFF, np.uint32)
     ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
     vol = oracle.fold(planes, trc)
     pos, d = S.random_rays(ob, 4000, seed=4)

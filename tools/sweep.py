@@ -1,0 +1,118 @@
+"""GPU exploration script (not part of the product): times kernel variants on the BASELINE configurations.
+usage: python tools/sweep.py [c5|c4|c2|ref|l2 ...]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import volumeraytracer_b200 as vrt
+from volumeraytracer_b200 import workloads as W
+
+dev = torch.device("cuda", 0)
+
+
+def timed(fn, reps=2):
+    best = 1e30
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    return best, out
+
+
+def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
+    res = []
+    for kver, block, refill, poll in variants:
+        co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)
+        co.set_option(vrt.VRT_OPT_REFILL, refill); co.set_option(vrt.VRT_OPT_STEPS_PER_POLL, poll)
+        t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
+        steps = int(out[2].to(torch.int64).sum().item())
+        print(json.dumps(dict(cfg=name, kver=kver, block=block, refill=refill, poll=poll, sec=round(t, 4), steps=steps,
+                              grays=round(steps / t / 1e9, 2))), flush=True)
+        res.append((steps / t / 1e9, kver, block, refill, poll))
+    return res
+
+
+VARIANTS = [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (3, 256, 0, 8), (3, 64, 0, 8), (3, 128, 32, 8), (3, 128, 16, 8),
+            (3, 128, 8, 8), (3, 128, 1, 8), (3, 128, 16, 2), (3, 128, 16, 32), (3, 256, 16, 8), (2, 128, 16, 8), (1, 128, 16, 8)]
+
+
+def cfg_c5(size=1024, nray=4096, iterations=2048):
+    ior = W.ior_c5_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
+    t0 = time.time(); sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    print("c5 scene prep %.2fs, volume %.2f GB" % (time.time() - t0, sc.volume_bytes / 1e9), flush=True)
+    del tr
+    pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c5_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    sc.close()
+
+
+def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
+    ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
+    tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_random(nrays, 8.0, size - 9.0, 0x5EED0004)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c4_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    sc.close()
+
+
+def cfg_c3(size=512, nray=2048, iterations=4096):
+    ior = W.ior_sines_torch(size, dev); tr = W.translucency_c3_torch(size, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_parallel_x(nray, nray, 4.0, size - 5.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c3_%d_live" % size, sc, tpos, tdir, iterations, VARIANTS, live=True)
+    sc.close()
+
+
+def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=True):
+    ior = W.ior_luneburg_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_parallel_x(nray, nray, 30.0, 225.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c2_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    if with_ref:
+        # the reference's own CUDA kernel (sm_100 build of the unmodified source) on the same rays, host buffers
+        from oracle import ref
+        if ref.available(cuda=True):
+            vol, trc = sc.download_volume()
+            planes = [np.ascontiguousarray(vol[:, a]) for a in range(3)]
+            rt = ref.RefTracer(sc._output_sizes, planes, trc, cuda=True)
+            p_h = tpos.cpu().numpy().view(np.uint32).reshape(-1, 3); d_h = tdir.cpu().numpy().reshape(-1, 3)
+            for rep in range(2):
+                t0 = time.time(); out = rt.trace(p_h, d_h, [1, 1, 1], 0, iterations); dt = time.time() - t0
+                steps = int(out[2].astype(np.int64).sum())
+                print(json.dumps(dict(cfg="c2_refcuda_hostcall", sec=round(dt, 3), steps=steps, grays=round(steps / dt / 1e9, 3))), flush=True)
+            # ours through the host-buffer call for the same comparison
+            sc.set_option(vrt.VRT_OPT_KERNEL, 3); sc.set_option(vrt.VRT_OPT_REFILL, 16)
+            for rep in range(2):
+                t0 = time.time(); mine = sc.trace_rays_cu(p_h, d_h, [1, 1, 1], 0, iterations); dt = time.time() - t0
+                print(json.dumps(dict(cfg="c2_ours_hostcall", sec=round(dt, 3), grays=round(steps / dt / 1e9, 3),
+                                      bit_exact_vs_refcuda=bool(all(np.array_equal(a, b) for a, b in zip(mine[:4], out[:4]))))), flush=True)
+    sc.close()
+
+
+def cfg_l2():
+    import ctypes as C
+    for mb in (16, 32, 48, 64, 256, 4096):
+        for sec in (32, 16):
+            g = C.c_double()
+            rc = vrt.lib().vrt_measure_gather_bandwidth(0, mb << 20, sec, 3, C.byref(g))
+            print(json.dumps(dict(cfg="gather", mb=mb, sector=sec, gbs=round(g.value, 1), rc=rc)), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
+    print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
+    for w in which:
+        {"c5": cfg_c5, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2}[w]()

@@ -1,0 +1,645 @@
+// vrt_api.cu -- host side of the C ABI declared in include/vrt_b200.h.
+//
+// Replaces, for the marcher path only, what the reference does in cuda_volume_raytracer.cu ("cu:"):
+//   TraceRaysCu ctor cu:644-720      -> vrt_scene_create*      (fold + interleave on the GPU, one upload)
+//   trace_rays_cu_impl cu:774-972    -> vrt_trace / vrt_trace_device (no AoS pack, no 32 768-ray chunking with
+//                                       cudaDeviceSynchronize between chunks, no per-call cudaMalloc/cudaFree of
+//                                       fixed buffers: stream-ordered allocations, whole-batch launches, copies
+//                                       pipelined against compute on two streams)
+//   ~TraceRaysCu cu:974-989          -> vrt_scene_destroy
+// There is deliberately no CPU path here (the reference falls back to trace_rays_cpu when num_rays <= 0x80 or no
+// device exists, cu:804-810): without a CUDA device every call fails with VRT_ERR_CUDA.
+
+#include "../../include/vrt_b200.h"
+#include "vrt_march.cuh"
+#include "vrt_prep.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace vrt;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define VRT_CUDA(call)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+        {                                                                                                   \
+            char buf__[512];                                                                                \
+            snprintf(buf__, sizeof buf__, "%s in %s at line %d (%d)", cudaGetErrorString(e__), __FILE__, __LINE__, (int)e__); \
+            cudaGetLastError();                                                                             \
+            return fail(e__ == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, buf__);            \
+        }                                                                                                   \
+    } while (0)
+
+struct DeviceGuard
+{
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// scene
+
+struct vrt_scene
+{
+    int       device = 0;
+    int       dim = 3;
+    uint64_t  bounds[3] = {1, 1, 1};   // cropped (gradient volume) extents
+    uint64_t  nvox = 0;
+    int       dtype = VRT_F32;
+    void     *d_volume = nullptr;
+    uint32_t *d_translucency = nullptr;
+    bool      owns = true;
+    // kept only by vrt_scene_create_from_ior, for vrt_normalise_rays_device (f2)
+    void     *d_ior = nullptr;
+    int       ior_dtype = VRT_F32;
+    uint64_t  ior_bounds[3] = {1, 1, 1};
+    bool      owns_ior = false;
+    int       num_sms = 148;
+    // options
+    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{16}, opt_chunk{0}, opt_poll{8};
+};
+
+static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
+
+static int check_geometry(int dim, const uint64_t *bounds, uint64_t *nvox)
+{
+    if (dim != 2 && dim != 3) return fail(VRT_ERR_INVALID, "Illegal dimension");                // cu:768-771
+    if (!bounds) return fail(VRT_ERR_INVALID, "bounds is null");
+    uint64_t n = 1;
+    for (int d = 0; d < dim; ++d)
+    {
+        if (bounds[d] < 2 || bounds[d] > 0xFFFF) return fail(VRT_ERR_INVALID, "bounds must be in [2, 65535] per axis (uint16 in the reference, cu:321)");
+        n *= bounds[d];
+    }
+    if (n >= (1ull << 32)) return fail(VRT_ERR_INVALID, "volume has >= 2^32 voxels (the reference indexes in uint32, cu:113)");
+    *nvox = n;
+    return VRT_OK;
+}
+
+static int new_scene(vrt_scene **out, int device, int dim, const uint64_t *bounds, int dtype)
+{
+    if (!out) return fail(VRT_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dtype != VRT_F32 && dtype != VRT_I16) return fail(VRT_ERR_INVALID, "diff_dtype must be VRT_F32 or VRT_I16");
+    uint64_t nvox = 0;
+    int rc = check_geometry(dim, bounds, &nvox);
+    if (rc) return rc;
+    int count = 0;
+    VRT_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(VRT_ERR_INVALID, "no such CUDA device");
+    vrt_scene *s = new vrt_scene();
+    s->device = device; s->dim = dim; s->dtype = dtype; s->nvox = nvox;
+    for (int d = 0; d < dim; ++d) s->bounds[d] = bounds[d];
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
+    *out = s;
+    return VRT_OK;
+}
+
+static int alloc_scene_buffers(vrt_scene *s)
+{
+    VRT_CUDA(cudaMalloc(&s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype)));
+    VRT_CUDA(cudaMalloc((void **)&s->d_translucency, s->nvox * sizeof(uint32_t)));
+    s->owns = true;
+    return VRT_OK;
+}
+
+extern "C" {
+
+const char *vrt_last_error(void) { return g_last_error.c_str(); }
+const char *vrt_version(void) { return "volumeraytracer_b200 0.1 (sm_100a)"; }
+uint64_t vrt_launch_count(void) { return g_launches.load(); }
+
+int vrt_device_count(int *count)
+{
+    if (!count) return fail(VRT_ERR_INVALID, "count is null");
+    *count = 0;
+    VRT_CUDA(cudaGetDeviceCount(count));
+    return VRT_OK;
+}
+
+int vrt_scene_destroy(vrt_scene *s)
+{
+    if (!s) return VRT_OK;
+    DeviceGuard g(s->device);
+    if (s->owns) { cudaFree(s->d_volume); cudaFree(s->d_translucency); }
+    if (s->owns_ior) cudaFree(s->d_ior);
+    cudaGetLastError();
+    delete s;
+    return VRT_OK;
+}
+
+int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                     const void *const *diff_planes, const uint32_t *translucency_cropped, unsigned flags)
+{
+    (void)flags;
+    if (!diff_planes || !translucency_cropped) return fail(VRT_ERR_INVALID, "null input");
+    for (int d = 0; d < dim && d < 3; ++d) if (!diff_planes[d]) return fail(VRT_ERR_INVALID, "null diff plane");
+    vrt_scene *s = nullptr;
+    int rc = new_scene(&s, device, dim, bounds, diff_dtype);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    rc = alloc_scene_buffers(s);
+    if (rc) { vrt_scene_destroy(s); return rc; }
+    const size_t es = elem_size(diff_dtype), plane_bytes = s->nvox * es;
+    void *tmp = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, plane_bytes * dim);
+    if (e != cudaSuccess) { vrt_scene_destroy(s); return fail(VRT_ERR_NOMEM, cudaGetErrorString(e)); }
+    for (int d = 0; d < dim; ++d)
+        e = e == cudaSuccess ? cudaMemcpy((char *)tmp + plane_bytes * d, diff_planes[d], plane_bytes, cudaMemcpyHostToDevice) : e;
+    e = e == cudaSuccess ? cudaMemcpy(s->d_translucency, translucency_cropped, s->nvox * 4, cudaMemcpyHostToDevice) : e;
+    if (e == cudaSuccess)
+    {
+        const unsigned blocks = (unsigned)((s->nvox + 255) / 256);
+        const char *t = (const char *)tmp;
+        if (diff_dtype == VRT_F32)
+            fold_kernel<float><<<blocks, 256>>>(dim, s->nvox, (const float *)t, (const float *)(t + plane_bytes), (const float *)(t + 2 * plane_bytes * (dim == 3)), s->d_translucency, (float *)s->d_volume);
+        else
+            fold_kernel<int16_t><<<blocks, 256>>>(dim, s->nvox, (const int16_t *)t, (const int16_t *)(t + plane_bytes), (const int16_t *)(t + 2 * plane_bytes * (dim == 3)), s->d_translucency, (int16_t *)s->d_volume);
+        ++g_launches;
+        e = cudaGetLastError();
+        e = e == cudaSuccess ? cudaDeviceSynchronize() : e;
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = s;
+    return VRT_OK;
+}
+
+int vrt_scene_create_interleaved(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                                 const void *volume_interleaved, const uint32_t *translucency_cropped, unsigned flags)
+{
+    (void)flags;
+    if (!volume_interleaved || !translucency_cropped) return fail(VRT_ERR_INVALID, "null input");
+    vrt_scene *s = nullptr;
+    int rc = new_scene(&s, device, dim, bounds, diff_dtype);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    rc = alloc_scene_buffers(s);
+    if (rc) { vrt_scene_destroy(s); return rc; }
+    cudaError_t e = cudaMemcpy(s->d_volume, volume_interleaved, s->nvox * (dim + 1) * elem_size(diff_dtype), cudaMemcpyHostToDevice);
+    e = e == cudaSuccess ? cudaMemcpy(s->d_translucency, translucency_cropped, s->nvox * 4, cudaMemcpyHostToDevice) : e;
+    if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = s;
+    return VRT_OK;
+}
+
+int vrt_scene_create_device(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
+                            const void *d_volume_interleaved, const uint32_t *d_translucency_cropped, unsigned flags)
+{
+    if (!d_volume_interleaved) return fail(VRT_ERR_INVALID, "null input");
+    vrt_scene *s = nullptr;
+    int rc = new_scene(&s, device, dim, bounds, diff_dtype);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (flags & VRT_SCENE_BORROW)
+    {
+        s->d_volume = const_cast<void *>(d_volume_interleaved);
+        s->d_translucency = const_cast<uint32_t *>(d_translucency_cropped);
+        s->owns = false;
+    }
+    else
+    {
+        rc = alloc_scene_buffers(s);
+        if (rc) { vrt_scene_destroy(s); return rc; }
+        cudaError_t e = cudaMemcpy(s->d_volume, d_volume_interleaved, s->nvox * (dim + 1) * elem_size(diff_dtype), cudaMemcpyDeviceToDevice);
+        if (d_translucency_cropped)
+            e = e == cudaSuccess ? cudaMemcpy(s->d_translucency, d_translucency_cropped, s->nvox * 4, cudaMemcpyDeviceToDevice) : e;
+        else
+            e = e == cudaSuccess ? cudaMemset(s->d_translucency, 0xFF, s->nvox * 4) : e;
+        if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = s;
+    return VRT_OK;
+}
+
+// stamp for derivative along `ax` (image_util.cpp:380-425): the base stamp differentiates along the LAST axis; the
+// stamp for axis ax is the base stamp with axes ax and dim-1 swapped; taps are visited in row-major order of the stamp.
+static void make_stamp(int dim, int ax, const uint64_t *ib, Stamp *st)
+{
+    static const int S3[27] = {-14, 0, 14, -47, 0, 47, -14, 0, 14, -47, 0, 47, -162, 0, 162, -47, 0, 47, -14, 0, 14, -47, 0, 47, -14, 0, 14};
+    static const int S2[9] = {-47, 0, 47, -162, 0, 162, -47, 0, 47};
+    const int *base = dim == 3 ? S3 : S2;
+    const int cnt = dim == 3 ? 27 : 9;
+    st->n = 0;
+    for (int j = 0; j < cnt; ++j)
+    {
+        int p[3] = {0, 0, 0}, r = j;
+        for (int d = dim - 1; d >= 0; --d) { p[d] = r % 3; r /= 3; }
+        int q[3] = {p[0], p[1], p[2]};
+        std::swap(q[ax], q[dim - 1]);
+        int lin = 0;
+        for (int d = 0; d < dim; ++d) lin = lin * 3 + q[d];
+        if (base[lin] == 0) continue;
+        long long off = 0;
+        for (int d = 0; d < dim; ++d) off = off * (long long)ib[d] + p[d];
+        st->off[st->n] = (int)off; st->val[st->n] = base[lin]; ++st->n;
+    }
+}
+
+int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64_t *bounds, int ior_dtype,
+                              const void *ior, const uint32_t *translucency, int ptrs_on_device, unsigned flags)
+{
+    (void)flags;
+    if (!ior || !translucency || !bounds) return fail(VRT_ERR_INVALID, "null input");
+    if (ior_dtype != VRT_F32 && ior_dtype != VRT_U32) return fail(VRT_ERR_INVALID, "ior_dtype must be VRT_F32 or VRT_U32");
+    if (dim != 2 && dim != 3) return fail(VRT_ERR_INVALID, "Illegal dimension: " + std::to_string(dim));   // image_util.cpp:558
+    uint64_t cb[3] = {1, 1, 1}, nin = 1;
+    for (int d = 0; d < dim; ++d)
+    {
+        if (bounds[d] < 4) return fail(VRT_ERR_INVALID, "bounds must be >= 4 per axis");
+        cb[d] = bounds[d] - 2; nin *= bounds[d];
+    }
+    if (nin >= (1ull << 31)) return fail(VRT_ERR_INVALID, "volume too large for the 32-bit stencil offsets");
+    vrt_scene *s = nullptr;
+    int rc = new_scene(&s, device, dim, cb, ior_dtype == VRT_F32 ? VRT_F32 : VRT_I16);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    rc = alloc_scene_buffers(s);
+    if (rc) { vrt_scene_destroy(s); return rc; }
+    s->ior_dtype = ior_dtype;
+    for (int d = 0; d < dim; ++d) s->ior_bounds[d] = bounds[d];
+
+    void *d_iorlog = nullptr; uint32_t *d_tr = nullptr; int *d_flag = nullptr;
+    cudaError_t e = cudaMalloc(&s->d_ior, nin * 4);
+    s->owns_ior = e == cudaSuccess;
+    e = e == cudaSuccess ? cudaMalloc(&d_iorlog, nin * 4) : e;
+    e = e == cudaSuccess ? cudaMalloc(&d_flag, 2 * sizeof(int)) : e;
+    e = e == cudaSuccess ? cudaMemset(d_flag, 0, 2 * sizeof(int)) : e;
+    const cudaMemcpyKind kind = ptrs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    e = e == cudaSuccess ? cudaMemcpy(s->d_ior, ior, nin * 4, kind) : e;
+    if (ptrs_on_device) d_tr = const_cast<uint32_t *>(translucency);
+    else
+    {
+        e = e == cudaSuccess ? cudaMalloc((void **)&d_tr, nin * 4) : e;
+        e = e == cudaSuccess ? cudaMemcpy(d_tr, translucency, nin * 4, cudaMemcpyHostToDevice) : e;
+    }
+    int flags_h[2] = {0, 0};
+    if (e == cudaSuccess)
+    {
+        PrepParams pp;
+        pp.dim = dim; pp.nin = nin; pp.nout = s->nvox;
+        for (int d = 0; d < 3; ++d) { pp.ib[d] = d < dim ? (uint32_t)bounds[d] : 1; pp.ob[d] = d < dim ? (uint32_t)cb[d] : 1; }
+        for (int a = 0; a < dim; ++a) make_stamp(dim, a, bounds, &pp.stamp[a]);
+        const unsigned bin = (unsigned)((nin + 255) / 256), bout = (unsigned)((s->nvox + 255) / 256);
+        if (ior_dtype == VRT_F32)
+        {
+            iorlog_f32_kernel<<<bin, 256>>>((const float *)s->d_ior, (float *)d_iorlog, nin, d_flag);
+            prep_f32_kernel<<<bout, 256>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
+        }
+        else
+        {
+            iorlog_u32_kernel<<<bin, 256>>>((const uint32_t *)s->d_ior, (int32_t *)d_iorlog, nin, d_flag);
+            prep_u32_kernel<<<bout, 256>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
+        }
+        g_launches += 2;
+        e = cudaGetLastError();
+        e = e == cudaSuccess ? cudaMemcpy(flags_h, d_flag, sizeof flags_h, cudaMemcpyDeviceToHost) : e;
+    }
+    cudaFree(d_iorlog); cudaFree(d_flag);
+    if (!ptrs_on_device) cudaFree(d_tr);
+    if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    if (flags_h[0]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "refraction-index underflow"); }   // image_util.cpp:536-541,607-610
+    if (flags_h[1]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "differention overflow"); }        // image_util.cpp:293-296
+    *out = s;
+    return VRT_OK;
+}
+
+int vrt_scene_info(const vrt_scene *s, int *device, int *dim, uint64_t *bounds, int *diff_dtype,
+                   void **d_volume_interleaved, uint32_t **d_translucency, uint64_t *volume_bytes)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    if (device) *device = s->device;
+    if (dim) *dim = s->dim;
+    if (bounds) for (int d = 0; d < s->dim; ++d) bounds[d] = s->bounds[d];
+    if (diff_dtype) *diff_dtype = s->dtype;
+    if (d_volume_interleaved) *d_volume_interleaved = s->d_volume;
+    if (d_translucency) *d_translucency = s->d_translucency;
+    if (volume_bytes) *volume_bytes = s->nvox * (s->dim + 1) * elem_size(s->dtype);
+    return VRT_OK;
+}
+
+int vrt_scene_download(const vrt_scene *s, void *host_volume, uint32_t *host_translucency)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    DeviceGuard g(s->device);
+    if (host_volume) VRT_CUDA(cudaMemcpy(host_volume, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToHost));
+    if (host_translucency && s->d_translucency) VRT_CUDA(cudaMemcpy(host_translucency, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToHost));
+    return VRT_OK;
+}
+
+int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    switch (key)
+    {
+    case VRT_OPT_KERNEL:         if (v < 0 || v > 3) return fail(VRT_ERR_INVALID, "kernel must be 0..3"); s->opt_kernel = v; break;
+    case VRT_OPT_BLOCK_THREADS:  if (v < 32 || v > 256 || v % 32) return fail(VRT_ERR_INVALID, "block threads must be a multiple of 32 in [32,256]"); s->opt_block = v; break;
+    case VRT_OPT_REFILL:         if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "refill threshold must be 0..32"); s->opt_refill = v; break;
+    case VRT_OPT_CHUNK_RAYS:     if (v < 0) return fail(VRT_ERR_INVALID, "chunk must be >= 0"); s->opt_chunk = v; break;
+    case VRT_OPT_STEPS_PER_POLL: if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "steps per poll must be 1..4096"); s->opt_poll = v; break;
+    default: return fail(VRT_ERR_INVALID, "unknown option");
+    }
+    return VRT_OK;
+}
+
+int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
+{
+    if (!s || !v) return fail(VRT_ERR_INVALID, "null argument");
+    switch (key)
+    {
+    case VRT_OPT_KERNEL: *v = s->opt_kernel; break;
+    case VRT_OPT_BLOCK_THREADS: *v = s->opt_block; break;
+    case VRT_OPT_REFILL: *v = s->opt_refill; break;
+    case VRT_OPT_CHUNK_RAYS: *v = s->opt_chunk; break;
+    case VRT_OPT_STEPS_PER_POLL: *v = s->opt_poll; break;
+    default: return fail(VRT_ERR_INVALID, "unknown option");
+    }
+    return VRT_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// launch
+
+template <typename VoxT, bool DIR_I16, bool LIVE, bool PATH, int KVER>
+static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, cudaStream_t st)
+{
+    auto kern = march3_kernel<VoxT, DIR_I16, LIVE, PATH, KVER>;
+    unsigned grid;
+    if (p.refill == 0) grid = (unsigned)((p.n + block - 1) / block);
+    else
+    {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const unsigned long long want = (p.n + block - 1) / block;
+        grid = (unsigned)std::min<unsigned long long>((unsigned long long)per_sm * s->num_sms, want);
+    }
+    kern<<<grid, block, 0, st>>>(p);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+template <typename VoxT, bool DIR_I16, bool LIVE>
+static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path, int kver, int block, cudaStream_t st)
+{
+    if (path) return launch3<VoxT, DIR_I16, LIVE, true, 2>(s, p, block, st);   // polyline output is store-bound: one variant
+    switch (kver)
+    {
+    case 1: return launch3<VoxT, DIR_I16, LIVE, false, 1>(s, p, block, st);
+    case 2: return launch3<VoxT, DIR_I16, LIVE, false, 2>(s, p, block, st);
+    default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
+    }
+}
+
+template <typename VoxT, bool DIR_I16, bool LIVE>
+static cudaError_t launch2_k(const MarchParams &p, bool path, int block, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((p.n + block - 1) / block);
+    if (path) march2_kernel<VoxT, DIR_I16, LIVE, true><<<grid, block, 0, st>>>(p);
+    else      march2_kernel<VoxT, DIR_I16, LIVE, false><<<grid, block, 0, st>>>(p);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+template <typename VoxT>
+static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir_i16, bool live, bool path, int kver, int block, cudaStream_t st)
+{
+    if (s->dim == 3)
+    {
+        if (dir_i16) return live ? launch3_k<VoxT, true, true>(s, p, path, kver, block, st) : launch3_k<VoxT, true, false>(s, p, path, kver, block, st);
+        return live ? launch3_k<VoxT, false, true>(s, p, path, kver, block, st) : launch3_k<VoxT, false, false>(s, p, path, kver, block, st);
+    }
+    if (dir_i16) return live ? launch2_k<VoxT, true, true>(p, path, block, st) : launch2_k<VoxT, true, false>(p, path, block, st);
+    return live ? launch2_k<VoxT, false, true>(p, path, block, st) : launch2_k<VoxT, false, false>(p, path, block, st);
+}
+
+static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const void *dir, int dir_dtype, const float *invscale,
+                          uint32_t iterations, unsigned flags, const void *epos, const void *edir, const void *eit, const void *light, const void *path)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    if (dir_dtype != VRT_F32 && dir_dtype != VRT_I16) return fail(VRT_ERR_INVALID, "dir_dtype must be VRT_F32 or VRT_I16");
+    if (!invscale) return fail(VRT_ERR_INVALID, "invscale is null");
+    if (n && (!pos || !dir || !epos || !edir || !eit || !light)) return fail(VRT_ERR_INVALID, "null ray buffer");
+    if ((flags & VRT_TRACE_PATHS) && n && !path) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs a path buffer");
+    if ((flags & VRT_TRACE_PATHS) && iterations == 0) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs iterations >= 1");
+    if ((flags & VRT_TRACE_LIVE_TRANSLUCENCY) && !s->d_translucency) return fail(VRT_ERR_INVALID, "scene has no translucency plane");
+    if (n >= (1ull << 40)) return fail(VRT_ERR_INVALID, "too many rays");
+    return VRT_OK;
+}
+
+// enqueue one marcher launch on `st`; `counter` is an 8-byte device scratch (zeroed here) or null for static mode
+static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
+                         uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
+                         uint32_t *d_light, uint32_t *d_path, unsigned long long *counter, cudaStream_t st)
+{
+    if (n == 0) return VRT_OK;
+    MarchParams p;
+    p.volume = s->d_volume; p.translucency = s->d_translucency;
+    p.by = (uint32_t)s->bounds[1]; p.bz = (uint32_t)s->bounds[2];
+    p.limx = (uint32_t)((s->bounds[0] - 1) & 0xFFFF); p.limy = (uint32_t)((s->bounds[1] - 1) & 0xFFFF); p.limz = (uint32_t)((s->bounds[2] - 1) & 0xFFFF);
+    p.invx = invscale[0]; p.invy = invscale[1]; p.invz = s->dim == 3 ? invscale[2] : 0.0f;
+    p.iterations = iterations; p.min_brightness = minb; p.n = n;
+    p.pos = d_pos; p.dir = d_dir; p.epos = d_epos; p.edir = d_edir; p.eit = d_eit; p.light = d_light; p.path = d_path;
+    p.steps_per_poll = (int)s->opt_poll.load();
+    p.refill = counter ? (int)s->opt_refill.load() : 0;
+    p.counter = counter;
+    int kver = (int)s->opt_kernel.load();
+    if (kver == 0) kver = 3;
+    const int block = (int)s->opt_block.load();
+    if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
+    cudaError_t e = s->dtype == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
+                                        : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
+    VRT_CUDA(e);
+    return VRT_OK;
+}
+
+extern "C" {
+
+int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
+                     uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
+                     uint32_t *d_light, uint32_t *d_path, void *cuda_stream)
+{
+    int rc = validate_trace(s, n, d_pos, d_dir, dir_dtype, invscale, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path);
+    if (rc) return rc;
+    DeviceGuard g(s->device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    unsigned long long *counter = nullptr;
+    const bool refill = s->opt_refill.load() > 0 && s->dim == 3;
+    if (refill) VRT_CUDA(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
+    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, counter, st);
+    if (counter) cudaFreeAsync(counter, st);
+    return rc;
+}
+
+int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, int dir_dtype, const float *invscale,
+              uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *epos, void *edir, uint32_t *eit, uint32_t *light, uint32_t *path)
+{
+    int rc = validate_trace(s, n, pos, dir, dir_dtype, invscale, iterations, flags, epos, edir, eit, light, path);
+    if (rc) return rc;
+    if (n == 0) return VRT_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    const int dim = s->dim;
+    const size_t ds = elem_size(dir_dtype);
+    const bool want_path = flags & VRT_TRACE_PATHS;
+    const bool refill = s->opt_refill.load() > 0 && dim == 3;
+
+    // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
+    uint64_t chunk = (uint64_t)s->opt_chunk.load();
+    if (chunk == 0) chunk = n <= (1u << 20) ? n : std::max<uint64_t>(1u << 20, (n + 7) / 8);
+    if (want_path)
+    {
+        const uint64_t per_ray = (uint64_t)iterations * dim * 4;
+        const uint64_t cap = std::max<uint64_t>(1, (1ull << 31) / std::max<uint64_t>(per_ray, 1));     // <= 2 GiB of polyline per chunk
+        chunk = std::min(chunk, cap);
+    }
+    cudaStream_t st[2] = {nullptr, nullptr};
+    VRT_CUDA(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(st[0]); return fail(VRT_ERR_CUDA, "cudaStreamCreate failed"); }
+
+    int result = VRT_OK;
+    int which = 0;
+    for (uint64_t off = 0; off < n && result == VRT_OK; off += chunk, which ^= 1)
+    {
+        const uint64_t m = std::min(chunk, n - off);
+        cudaStream_t q = st[which];
+        char *buf = nullptr;
+        // one stream-ordered allocation per chunk: [pos | dir | eit | light | counter | path]
+        const size_t b_pos = (size_t)m * dim * 4, b_dir = (size_t)m * dim * ds, b_u32 = (size_t)m * 4;
+        const size_t o_dir = (b_pos + 255) & ~(size_t)255, o_eit = (o_dir + b_dir + 255) & ~(size_t)255, o_light = (o_eit + b_u32 + 255) & ~(size_t)255;
+        const size_t o_cnt = (o_light + b_u32 + 255) & ~(size_t)255, o_path = o_cnt + 256;
+        const size_t b_path = want_path ? (size_t)m * iterations * dim * 4 : 0;
+        cudaError_t e = cudaMallocAsync((void **)&buf, o_path + b_path, q);
+        if (e != cudaSuccess) { result = fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); break; }
+        uint32_t *d_pos = (uint32_t *)buf; void *d_dir = buf + o_dir;
+        uint32_t *d_eit = (uint32_t *)(buf + o_eit), *d_light = (uint32_t *)(buf + o_light), *d_path = want_path ? (uint32_t *)(buf + o_path) : nullptr;
+        e = cudaMemcpyAsync(d_pos, pos + off * dim, b_pos, cudaMemcpyHostToDevice, q);
+        e = e == cudaSuccess ? cudaMemcpyAsync(d_dir, (const char *)dir + off * dim * ds, b_dir, cudaMemcpyHostToDevice, q) : e;
+        if (e == cudaSuccess)
+        {
+            // results overwrite the start buffers on the device ("written back in place")
+            int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, d_path,
+                                    refill ? (unsigned long long *)(buf + o_cnt) : nullptr, q);
+            if (rc2) { result = rc2; }
+        }
+        if (result == VRT_OK)
+        {
+            e = e == cudaSuccess ? cudaMemcpyAsync(epos + off * dim, d_pos, b_pos, cudaMemcpyDeviceToHost, q) : e;
+            e = e == cudaSuccess ? cudaMemcpyAsync((char *)edir + off * dim * ds, d_dir, b_dir, cudaMemcpyDeviceToHost, q) : e;
+            e = e == cudaSuccess ? cudaMemcpyAsync(eit + off, d_eit, b_u32, cudaMemcpyDeviceToHost, q) : e;
+            e = e == cudaSuccess ? cudaMemcpyAsync(light + off, d_light, b_u32, cudaMemcpyDeviceToHost, q) : e;
+            if (want_path) e = e == cudaSuccess ? cudaMemcpyAsync(path + off * iterations * dim, d_path, b_path, cudaMemcpyDeviceToHost, q) : e;
+        }
+        cudaFreeAsync(buf, q);
+        if (e != cudaSuccess && result == VRT_OK) { result = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
+    }
+    for (int i = 0; i < 2; ++i)
+    {
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && result == VRT_OK) { result = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
+        cudaStreamDestroy(st[i]);
+    }
+    return result;
+}
+
+int vrt_normalise_rays_device(vrt_scene *s, uint64_t n, uint32_t *d_pos, void *d_dir, int dir_dtype, int64_t *first_bad_ray, void *cuda_stream)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    if (!s->d_ior) return fail(VRT_ERR_UNSUPPORTED, "scene was not created from an ior volume");
+    if ((s->ior_dtype == VRT_F32) != (dir_dtype == VRT_F32))
+        return fail(VRT_ERR_UNSUPPORTED, "the reference instantiates float scene/float dirs and int16 scene/int16 dirs only (image_util.cpp:914-955)");
+    if (first_bad_ray) *first_bad_ray = 0;
+    if (n == 0) return VRT_OK;
+    if (!d_pos || !d_dir) return fail(VRT_ERR_INVALID, "null ray buffer");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    unsigned long long *d_flags = nullptr;
+    VRT_CUDA(cudaMallocAsync((void **)&d_flags, 16, st));
+    VRT_CUDA(cudaMemsetAsync(d_flags, 0xFF, 16, st));
+    NormParams np;
+    np.dim = s->dim; np.n = n;
+    for (int d = 0; d < 3; ++d) np.ib[d] = d < s->dim ? (uint32_t)s->ior_bounds[d] : 1;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (s->ior_dtype == VRT_F32) normalise_kernel<true><<<grid, 256, 0, st>>>(np, s->d_ior, d_pos, d_dir, d_flags, d_flags + 1);
+    else                         normalise_kernel<false><<<grid, 256, 0, st>>>(np, s->d_ior, d_pos, d_dir, d_flags, d_flags + 1);
+    ++g_launches;
+    VRT_CUDA(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    VRT_CUDA(cudaMemcpyAsync(h, d_flags, 16, cudaMemcpyDeviceToHost, st));
+    VRT_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_flags, st);
+    if (h[0] != ~0ull)
+    {
+        if (first_bad_ray) *first_bad_ray = (int64_t)h[0];
+        return fail(VRT_ERR_INVALID, "ray " + std::to_string(h[0] - 1) + " is not in 0 to bounds");          // image_util.cpp:686-691
+    }
+    if (h[1] != ~0ull) return fail(VRT_ERR_INVALID, "Normalize length failed (ray " + std::to_string(h[1] - 1) + ")"); // image_util.cpp:703
+    return VRT_OK;
+}
+
+int vrt_measure_gather_bandwidth(int device, uint64_t bytes, int sector_bytes, int iters, double *gb_per_s)
+{
+    if (!gb_per_s || (sector_bytes != 16 && sector_bytes != 32) || bytes < 4096 || iters < 1) return fail(VRT_ERR_INVALID, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    VRT_CUDA(cudaGetDeviceProperties(&prop, device));
+    uint4 *buf = nullptr; unsigned long long *sink = nullptr;
+    VRT_CUDA(cudaMalloc((void **)&buf, bytes));
+    VRT_CUDA(cudaMalloc((void **)&sink, 8));
+    VRT_CUDA(cudaMemset(buf, 1, bytes));
+    const unsigned long long nsectors = bytes / sector_bytes;
+    const int block = 256, grid = prop.multiProcessorCount * 8, rounds = 64;
+    cudaEvent_t a, b;
+    VRT_CUDA(cudaEventCreate(&a)); VRT_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int it = 0; it < iters + 2; ++it)
+    {
+        VRT_CUDA(cudaEventRecord(a));
+        if (sector_bytes == 32) gather_kernel<32><<<grid, block>>>(buf, nsectors, rounds, sink);
+        else                    gather_kernel<16><<<grid, block>>>(buf, nsectors, rounds, sink);
+        ++g_launches;
+        VRT_CUDA(cudaEventRecord(b));
+        VRT_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (it >= 2) best = std::min(best, ms);
+    }
+    const double moved = (double)grid * block * rounds * 8.0 * sector_bytes;
+    *gb_per_s = moved / (best * 1e-3) / 1e9;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    return VRT_OK;
+}
+
+} // extern "C"

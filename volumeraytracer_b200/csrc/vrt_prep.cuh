@@ -1,0 +1,246 @@
+// vrt_prep.cuh -- the two thin steps either side of the marcher, on the GPU ("next" rows f1, f2).
+//
+// f1  scene prep  (reference: RaytraceScene ctor image_util.cpp:501-643, convolution :239-298, stamps :421-425,
+//                  TraceRaysCu ctor cuda_volume_raytracer.cu:654-669)
+//       iorlog = log(n) * 0x420000; gradient = 3x3x3 {14,47,162} stencil / (812*256) per axis on the volume
+//       shrunk by one voxel per face; extra channel = (0x7FFFFFFF - translucency)/0x10000; interleave.
+// f2  ray pre-processing (reference: RaytraceScene::trace_rays image_util.cpp:675-719, interpolator image_util.h:348-431)
+//
+// Operation order follows what the reference's g++ build executes (checked bit for bit through
+// oracle/vrt_oracle.c against oracle/_ref): the float stencil sum is a plain mul + add chain (not fused), the
+// float interpolator is r = fma(lo, wl, hi*wr).  The only tolerated deviation is libm: log() of the device
+// vs glibc may differ in the last double ulp, which survives the narrowing to float / int32 about once per
+// 2^29 voxels.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vrt {
+
+struct Stamp
+{
+    int n;            // number of non-zero taps (18 in 3-D, 6 in 2-D)
+    int off[18];      // element offset inside the uncropped volume, relative to the 3^dim block's origin
+    int val[18];      // tap weight
+};
+
+struct PrepParams
+{
+    int      dim;
+    uint32_t ib[3];   // uncropped bounds (padded at the FRONT with 1 for dim == 2 is NOT done: ib[0..dim-1])
+    uint32_t ob[3];   // cropped bounds = ib - 2
+    unsigned long long nin, nout;
+    Stamp    stamp[3];
+};
+
+// log(n) * 0x420000 -- float scene: image_util.cpp:611 (double log, double product, narrowed on store)
+__global__ void iorlog_f32_kernel(const float *ior, float *iorlog, unsigned long long n, int *bad)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = ior[i];
+    if (!(v > 0.0f)) { *bad = 1; iorlog[i] = 0.0f; return; }
+    iorlog[i] = (float)(log((double)v) * (double)0x420000);
+}
+
+// int16 scene: image_util.cpp:532-543 (round to nearest, ties away)
+__global__ void iorlog_u32_kernel(const uint32_t *ior, int32_t *iorlog, unsigned long long n, int *bad)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double fior = (double)ior[i] / (double)0x10000;
+    double tmp = log(fior) * (double)0x420000;
+    if (!(tmp <= 2147483647.0) || !(tmp >= -2147483648.0)) { *bad = 1; iorlog[i] = 0; return; }
+    iorlog[i] = (int32_t)round(tmp);
+}
+
+__device__ __forceinline__ unsigned long long in_base(const PrepParams &p, unsigned long long o, uint32_t c[3])
+{
+    // output voxel o -> coordinates c (axis 0 slowest) and the element offset of the stencil block's origin
+    unsigned long long r = o, base = 0, mul = 1;
+    for (int d = p.dim - 1; d >= 0; --d)
+    {
+        c[d] = (uint32_t)(r % p.ob[d]); r /= p.ob[d];
+        base += (unsigned long long)c[d] * mul; mul *= p.ib[d];
+    }
+    return base;
+}
+
+__device__ __forceinline__ unsigned long long centre_offset(const PrepParams &p)
+{
+    unsigned long long off = 0, mul = 1;
+    for (int d = p.dim - 1; d >= 0; --d) { off += mul; mul *= p.ib[d]; }
+    return off;
+}
+
+// one thread per cropped voxel: dim gradient channels + extra channel, interleaved; also the cropped translucency plane
+__global__ void prep_f32_kernel(const PrepParams p, const float *iorlog, const uint32_t *translucency,
+                                float *volume, uint32_t *tr_cropped)
+{
+    unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= p.nout) return;
+    uint32_t c[3];
+    const unsigned long long base = in_base(p, o, c);
+    const float weight = 812.0f * 256.0f;                                  // image_util.cpp:438
+    float out[4];
+    for (int ax = 0; ax < p.dim; ++ax)
+    {
+        float sum = 0.0f;
+        for (int j = 0; j < p.stamp[ax].n; ++j)                            // image_util.cpp:284-287: sum += w * in
+            sum = __fadd_rn(sum, __fmul_rn((float)p.stamp[ax].val[j], iorlog[base + p.stamp[ax].off[j]]));
+        out[ax] = __fdiv_rn(sum, weight);                                  // :288-291
+    }
+    const uint32_t tr = translucency[base + centre_offset(p)];             // crop_matrix :300-319, lower bound 1
+    tr_cropped[o] = tr;
+    out[p.dim] = (float)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);   // cu:654-659
+    float *dst = volume + o * (unsigned long long)(p.dim + 1);
+    for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+}
+
+__device__ __forceinline__ int32_t div_round_closest(int32_t n, int32_t d) // image_util.h:34-38
+{
+    return ((n < 0) ^ (d < 0)) ? ((n - d / 2) / d) : ((n + d / 2) / d);
+}
+
+__global__ void prep_u32_kernel(const PrepParams p, const int32_t *iorlog, const uint32_t *translucency,
+                                int16_t *volume, uint32_t *tr_cropped, int *overflow)
+{
+    unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= p.nout) return;
+    uint32_t c[3];
+    const unsigned long long base = in_base(p, o, c);
+    const int32_t weight = 812 * 256;
+    int16_t out[4];
+    for (int ax = 0; ax < p.dim; ++ax)
+    {
+        uint32_t sum = 0;                                                  // int32 accumulate (wraps like the reference's)
+        for (int j = 0; j < p.stamp[ax].n; ++j)
+            sum += (uint32_t)(p.stamp[ax].val[j] * iorlog[base + p.stamp[ax].off[j]]);
+        const int32_t v = div_round_closest((int32_t)sum, weight);
+        out[ax] = (int16_t)v;
+        if ((int32_t)out[ax] != v) *overflow = 1;                          // "differention overflow" :293-296
+    }
+    const uint32_t tr = translucency[base + centre_offset(p)];
+    tr_cropped[o] = tr;
+    out[p.dim] = (int16_t)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);
+    int16_t *dst = volume + o * (unsigned long long)(p.dim + 1);
+    for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+}
+
+// TraceRaysCu ctor on planar inputs (cu:654-669): extra channel + interleave
+template <typename T>
+__global__ void fold_kernel(int dim, unsigned long long nvox, const T *d0, const T *d1, const T *d2, const uint32_t *tr, T *out)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvox) return;
+    T *dst = out + i * (unsigned long long)(dim + 1);
+    dst[0] = d0[i];
+    dst[1] = d1[i];
+    if (dim == 3) dst[2] = d2[i];
+    dst[dim] = (T)((long long)(0x7FFFFFFFll - (long long)tr[i]) / 0x10000ll);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// f2: ray normalisation
+
+struct NormParams
+{
+    int      dim;
+    uint32_t ib[3];                  // uncropped bounds
+    unsigned long long n;
+};
+
+__device__ __forceinline__ unsigned long long corner_index(const NormParams &p, const uint32_t *pos, int k)
+{
+    unsigned long long idx = 0;
+    for (int d = 0; d < p.dim; ++d) idx = idx * p.ib[d] + (pos[d] >> 16) + (unsigned)((k >> (p.dim - 1 - d)) & 1);
+    return idx;
+}
+
+template <bool IOR_F32>
+__global__ void normalise_kernel(const NormParams p, const void *ior, uint32_t *pos, void *dir, unsigned long long *first_bad,
+                                 unsigned long long *first_overflow)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    uint32_t q[3];
+    bool ok = true;
+    for (int d = 0; d < p.dim; ++d)
+    {
+        q[d] = pos[i * p.dim + d];
+        // image_util.cpp:686: lhs < 0x10000 || lhs + 1 >= rhs * 0x10000
+        if ((unsigned long long)q[d] < 0x10000ull || (unsigned long long)q[d] + 1ull >= (unsigned long long)p.ib[d] * 0x10000ull) ok = false;
+    }
+    if (!ok) { atomicMin(first_bad, i + 1ull); return; }
+    for (int d = 0; d < p.dim; ++d) q[d] -= 0x8000u;
+    const int cnt = 1 << p.dim;
+    if (IOR_F32)
+    {
+        float v[8];
+        for (int k = 0; k < cnt; ++k) v[k] = ((const float *)ior)[corner_index(p, q, k)];
+        int h = cnt;
+        for (int d = 0; d < p.dim; ++d)
+        {
+            const float fr = (float)(q[d] & 0xFFFFu), fl = (float)(0x10000u - (q[d] & 0xFFFFu));
+            h >>= 1;
+            for (int k = 0; k < h; ++k) v[k] = __fmaf_rn(v[k], fl, __fmul_rn(v[k + h], fr));       // image_util.h:421-424
+        }
+        const float nn = __fmul_rn(v[0], p.dim == 3 ? 1.0f / 0x1000000000000p0f : 1.0f / 0x100000000p0f);
+        float *dd = (float *)dir + i * p.dim;
+        for (int d = 0; d < p.dim; ++d) dd[d] = __fmul_rn(dd[d], nn);                               // image_util.cpp:697
+    }
+    else
+    {
+        uint32_t v[8];
+        for (int k = 0; k < cnt; ++k) v[k] = ((const uint32_t *)ior)[corner_index(p, q, k)];
+        int h = cnt;
+        for (int d = 0; d < p.dim; ++d)
+        {
+            const unsigned long long mr = q[d] & 0xFFFFu, ml = 0x10000ull - mr;
+            h >>= 1;
+            for (int k = 0; k < h; ++k) v[k] = (uint32_t)(((unsigned long long)v[k] * ml + (unsigned long long)v[k + h] * mr + 0x8000ull) / 0x10000ull);
+        }
+        const long long nn = (long long)v[0];
+        short *dd = (short *)dir + i * p.dim;
+        for (int d = 0; d < p.dim; ++d)
+        {
+            const long long num = (long long)dd[d] * nn, den = 0x10000;
+            const long long t = (num < 0) ? ((num - den / 2) / den) : ((num + den / 2) / den);      // divRoundClosest, image_util.cpp:701
+            if (t > 32767 || t < -32768) atomicMin(first_overflow, i + 1ull);                       // "Normalize length failed"
+            dd[d] = (short)t;
+        }
+    }
+    for (int d = 0; d < p.dim; ++d) pos[i * p.dim + d] = q[d] - 0x8000u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// roofline helper: random sector gather (SURVEY.md section 8d asks for a measured L2 gather bandwidth)
+
+template <int SECTOR_BYTES>
+__global__ void gather_kernel(const uint4 *buf, unsigned long long nsectors, int rounds, unsigned long long *sink)
+{
+    unsigned long long x = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    unsigned acc = 0;
+    for (int r = 0; r < rounds; ++r)
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+        {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;                 // xorshift64*
+            const unsigned long long s = ((x * 0x2545F4914F6CDD1Dull) >> 11) % nsectors;
+            const uint4 *ptr = buf + s * (SECTOR_BYTES / 16);
+            uint4 a;
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(ptr));
+            acc += a.x ^ a.w;
+            if (SECTOR_BYTES == 32)
+            {
+                asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(ptr + 1));
+                acc += a.y ^ a.z;
+            }
+        }
+    }
+    if (acc == 0x7FFFFFFFu) *sink = acc;
+}
+
+} // namespace vrt

@@ -172,3 +172,67 @@ def rays_random(n, lo, hi, seed, dim=3):
 
 def dirs_to_i16(d):
     return np.clip(np.rint(np.asarray(d, dtype=np.float64) * 256.0), -32768, 32767).astype(np.int16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# torch twins of the large analytic fields (produced on the GPU: 512^3 / 1024^3 are too slow in numpy).
+# Values can differ from the numpy versions in the last float32 ulp (different sin/cos); whoever needs
+# identical bits on the CPU side (oracle, cpu_baseline) downloads the staged volume from the device.
+
+def ior_c5_torch(size, device, base=1.2, amp=0.05, period=256.0):
+    import torch
+    t = torch.arange(size, dtype=torch.float32, device=device) * float(2.0 * np.pi / period)
+    s, c = torch.sin(t), torch.cos(t)
+    return (base + amp * s[:, None, None] * c[None, :, None] * c[None, None, :]).contiguous()
+
+
+def ior_sines_torch(size, device, base=1.3, amp=0.1, period=128.0):
+    import torch
+    s = torch.sin(torch.arange(size, dtype=torch.float32, device=device) * float(2.0 * np.pi / period))
+    return (base + amp * s[:, None, None] * s[None, :, None] * s[None, None, :]).contiguous()
+
+
+def ior_luneburg_torch(size, device, radius=100.0):
+    import torch
+    c = (size - 1) / 2.0
+    g = torch.arange(size, dtype=torch.float32, device=device) - c
+    r2 = (g * g)[:, None, None] + (g * g)[None, :, None] + (g * g)[None, None, :]
+    return torch.sqrt(torch.clamp(2.0 - r2 / float(radius * radius), min=1.0)).contiguous()
+
+
+def translucency_c3_torch(size, device):
+    """uint32 plane held in an int32 tensor (bit pattern)."""
+    import torch
+    x = torch.arange(size, dtype=torch.float64, device=device)
+    ax = 1.0 + torch.cos(2.0 * np.pi * x / 64.0)
+    ay = x / (size - 1.0)
+    absorb = torch.floor((1 << 21) * ay[None, :, None] * ax[:, None, None]).to(torch.int64)
+    tr = (0xFFFFFFFF - absorb).expand(size, size, size).clone()
+    c = (size - 1) / 2.0
+    g = torch.arange(size, dtype=torch.float32, device=device) - c
+    r2 = (g * g)[:, None, None] + (g * g)[None, :, None] + (g * g)[None, None, :]
+    tr[r2 < (40.0 * size / 512.0) ** 2] = 0
+    return (tr & 0xFFFFFFFF).to(torch.int64).where(tr < 0x80000000, tr - (1 << 32)).to(torch.int32).contiguous()
+
+
+def solve_harmonic_torch(size, device, inner_radius, inner_value=1.6, face_value=1.0, sweeps=300):
+    import torch
+    v = torch.full((size,) * 3, face_value, dtype=torch.float32, device=device)
+    c = (size - 1) / 2.0
+    g = torch.arange(size, dtype=torch.float32, device=device) - c
+    r2 = (g * g)[:, None, None] + (g * g)[None, :, None] + (g * g)[None, None, :]
+    ball = r2 < float(inner_radius ** 2)
+    v[ball] = inner_value
+    free = ~ball[1:-1, 1:-1, 1:-1]
+    for _ in range(sweeps):
+        m = (v[:-2, 1:-1, 1:-1] + v[2:, 1:-1, 1:-1] + v[1:-1, :-2, 1:-1] + v[1:-1, 2:, 1:-1]
+             + v[1:-1, 1:-1, :-2] + v[1:-1, 1:-1, 2:]) * (1.0 / 6.0)
+        inner = v[1:-1, 1:-1, 1:-1]
+        v = v.clone()
+        v[1:-1, 1:-1, 1:-1] = torch.where(free, m, inner)
+    return v.contiguous()
+
+
+def clear_translucency_torch(shape, device):
+    import torch
+    return torch.full(tuple(shape), -1, dtype=torch.int32, device=device)

@@ -212,7 +212,7 @@ def translucency_c3_torch(size, device):
     g = torch.arange(size, dtype=torch.float32, device=device) - c
     r2 = (g * g)[:, None, None] + (g * g)[None, :, None] + (g * g)[None, None, :]
     tr[r2 < (40.0 * size / 512.0) ** 2] = 0
-    return (tr & 0xFFFFFFFF).to(torch.int64).where(tr < 0x80000000, tr - (1 << 32)).to(torch.int32).contiguous()
+    return torch.where(tr >= (1 << 31), tr - (1 << 32), tr).to(torch.int32).contiguous()
 
 
 def solve_harmonic_torch(size, device, inner_radius, inner_value=1.6, face_value=1.0, sweeps=300):

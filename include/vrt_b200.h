@@ -107,6 +107,9 @@ VRT_API int vrt_scene_info(const vrt_scene *scene, int *device, int *dim, uint64
 /* Copy the staged volume back to the host (the reference keeps such a host copy itself: _diff_interleaved,
  * cuda_volume_raytracer.h:67).  host_volume: volume_bytes; host_translucency: nvox uint32; either may be NULL. */
 VRT_API int vrt_scene_download(const vrt_scene *scene, void *host_volume, uint32_t *host_translucency);
+/* Device-to-device copy of the staged volume into caller buffers on the scene's device (what rank 0 hands to
+ * ncclBroadcast in the multi-GPU set-up; the reference instead re-uploads from the host per device, cu:676-686). */
+VRT_API int vrt_scene_export_device(const vrt_scene *scene, void *d_volume_out, uint32_t *d_translucency_out, void *cuda_stream);
 VRT_API int vrt_scene_set_option(vrt_scene *scene, int key, int64_t value);
 VRT_API int vrt_scene_get_option(const vrt_scene *scene, int key, int64_t *value);
 

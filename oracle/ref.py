@@ -13,18 +13,27 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_ref.so")
 # (trace_rays_gpu, cu:397-414) for more than 0x80 rays -- the GPU-side comparator on the B200 box
 CUDA_LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_ref_cuda.so")
 
+# the reference's UNMODIFIED image_util/util/io_util/serialize objects linked against OUR TraceRaysCu<> drop-in
+# (volumeraytracer_b200/csrc/trace_rays_cu_dropin.cpp -> libvrt_b200.so): RefScene(..., which="dropin") then runs the
+# reference's C++ API with the B200 marcher underneath
+DROPIN_LIB_PATH = os.path.join(_HERE, "_ref", "libvrt_dropin.so")
+
 _libs = {}
 
 
+def _path(which):
+    return {False: LIB_PATH, "cpu": LIB_PATH, True: CUDA_LIB_PATH, "cuda": CUDA_LIB_PATH, "dropin": DROPIN_LIB_PATH}[which]
+
+
 def available(cuda=False):
-    return os.path.exists(CUDA_LIB_PATH if cuda else LIB_PATH)
+    return os.path.exists(_path(cuda))
 
 
 def lib(cuda=False):
     if cuda not in _libs:
         if not available(cuda):
             raise RuntimeError("reference harness not built: run `make -C oracle ref ref_cuda` where /root/reference exists")
-        l = C.CDLL(CUDA_LIB_PATH if cuda else LIB_PATH)
+        l = C.CDLL(_path(cuda))
         l.vrtref_last_error.restype = C.c_char_p
         _libs[cuda] = l
     return _libs[cuda]
@@ -50,7 +59,8 @@ class RefScene:
     """Reference RaytraceScene<float,float,float> (ior float32) or <ior_t,iorlog_t,diff_t> (ior uint32).
     image_util.cpp:501-643 (ctor), :645-772 (trace_rays)."""
 
-    def __init__(self, bounds, ior, translucency, loglevel=0):
+    def __init__(self, bounds, ior, translucency, loglevel=0, which=False):
+        self.which = which
         self.bounds = np.asarray(bounds, dtype=np.uint64)
         self.dim = len(self.bounds)
         ior = np.ascontiguousarray(ior).reshape(-1)
@@ -59,17 +69,17 @@ class RefScene:
         if self.kind == "u32":
             ior = ior.astype(np.uint32, copy=False)
         self.h = C.c_void_p()
-        fn = getattr(lib(), "vrtref_scene_new_" + self.kind)
-        _check(fn(C.byref(self.h), _p(self.bounds), self.dim, _p(ior), _p(tr), loglevel))
+        fn = getattr(lib(self.which), "vrtref_scene_new_" + self.kind)
+        _check(fn(C.byref(self.h), _p(self.bounds), self.dim, _p(ior), _p(tr), loglevel), self.which)
         db = np.zeros(self.dim, dtype=np.uint64)
-        getattr(lib(), "vrtref_scene_diff_bounds_" + self.kind)(self.h, _p(db))
+        getattr(lib(self.which), "vrtref_scene_diff_bounds_" + self.kind)(self.h, _p(db))
         self.diff_bounds = db
         self.diff_dtype = np.float32 if self.kind == "f32" else np.int16
         self.dir_dtype = np.float32 if self.kind == "f32" else np.int16
 
     def close(self):
         if self.h:
-            getattr(lib(), "vrtref_scene_delete_" + self.kind)(self.h)
+            getattr(lib(self.which), "vrtref_scene_delete_" + self.kind)(self.h)
             self.h = None
 
     def __del__(self):
@@ -84,22 +94,22 @@ class RefScene:
 
     def interleaved(self):
         out = np.zeros((self.nvox, self.dim + 1), dtype=self.diff_dtype)
-        getattr(lib(), "vrtref_scene_interleaved_" + self.kind)(self.h, _p(out))
+        getattr(lib(self.which), "vrtref_scene_interleaved_" + self.kind)(self.h, _p(out))
         return out
 
     def diff(self, axis):
         out = np.zeros(self.nvox, dtype=self.diff_dtype)
-        getattr(lib(), "vrtref_scene_diff_" + self.kind)(self.h, axis, _p(out))
+        getattr(lib(self.which), "vrtref_scene_diff_" + self.kind)(self.h, axis, _p(out))
         return out
 
     def iorlog(self):
         out = np.zeros(int(np.prod(self.bounds)), dtype=np.float32 if self.kind == "f32" else np.int32)
-        getattr(lib(), "vrtref_scene_iorlog_" + self.kind)(self.h, _p(out))
+        getattr(lib(self.which), "vrtref_scene_iorlog_" + self.kind)(self.h, _p(out))
         return out
 
     def translucency_cropped(self):
         out = np.zeros(self.nvox, dtype=np.uint32)
-        getattr(lib(), "vrtref_scene_translucency_cropped_" + self.kind)(self.h, _p(out))
+        getattr(lib(self.which), "vrtref_scene_translucency_cropped_" + self.kind)(self.h, _p(out))
         return out
 
     def trace(self, pos, dir, invscale, min_brightness, iterations, trace_path=False, max_cpu=0):
@@ -110,9 +120,9 @@ class RefScene:
         epos = np.zeros_like(pos); edir = np.zeros_like(dir)
         eit = np.zeros(n, dtype=np.uint32); light = np.zeros(n, dtype=np.uint32)
         path = np.zeros((n, iterations, self.dim), dtype=np.uint32) if trace_path else None
-        fn = getattr(lib(), "vrtref_scene_trace_" + self.kind)
+        fn = getattr(lib(self.which), "vrtref_scene_trace_" + self.kind)
         _check(fn(self.h, C.c_size_t(n), _p(pos), _p(dir), _p(isc), C.c_uint32(min_brightness), C.c_uint32(iterations),
-                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
+                  int(trace_path), int(max_cpu), _p(epos), _p(edir), _p(eit), _p(light), _p(path)), self.which)
         return epos, edir, eit, light, path
 
 
@@ -168,7 +178,7 @@ def trace_live(volume, translucency, bounds, invscale, pos, dir, iterations, min
     dim = len(bounds)
     volume = np.ascontiguousarray(volume)
     vk = _DIR[volume.dtype]
-    tr = np.ascontiguousarray(translucency, dtype=np.uint32).reshape(-1)
+    tr = np.ascontiguousarray(translucency, dtype=np.uint32).reshape(-1) if translucency is not None else None   # None: shipped (compiled-out) variant
     pos = np.ascontiguousarray(pos, dtype=np.uint32).reshape(-1, dim)
     dir = np.ascontiguousarray(dir).reshape(-1, dim)
     dk = _DIR[dir.dtype]

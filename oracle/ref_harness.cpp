@@ -109,7 +109,11 @@ int trace_live_dim(DiffType *vol, const uint32_t *tr, const size_t *bounds, cons
     for (size_t i = 0; i < n; i += chunk)
     {
         size_t m = std::min(chunk, n - i);
-        if (trace_path)
+        if (!trp && trace_path)
+            trace_rays_cpu(vol, DummyArray(), osz, isc, ray_data.data() + i, reinterpret_cast<cuda_tuple<pos_t,dim>*>(path) + i * iterations, iterations, DummyObject(), m, (size_t)threads);
+        else if (!trp)
+            trace_rays_cpu(vol, DummyArray(), osz, isc, ray_data.data() + i, DummyArray(), iterations, DummyObject(), m, (size_t)threads);
+        else if (trace_path)
             trace_rays_cpu(vol, trp, osz, isc, ray_data.data() + i, reinterpret_cast<cuda_tuple<pos_t,dim>*>(path) + i * iterations, iterations, mb, m, (size_t)threads);
         else
             trace_rays_cpu(vol, trp, osz, isc, ray_data.data() + i, DummyArray(), iterations, mb, m, (size_t)threads);
@@ -168,6 +172,8 @@ int NAME(const DIFF *vol, const uint32_t *tr, const size_t *bounds, int dim, con
     if (dim == 2) return trace_live_dim<DIFF, DIR, 2>(const_cast<DIFF*>(vol), tr, bounds, invscale, n, pos, dir, iterations, minb, trace_path, threads, epos, edir, eit, light, path); \
     vrtref_set_error("Illegal dimension"); return -1;                                                                                        \
 }
+// tr == NULL: the SHIPPED instantiation (DummyArray translucency, DummyObject brightness: cu:916-941) run directly on a
+// caller-provided interleaved volume, i.e. trace_rays_cu_impl without the ctor's extra host copy of the volume.
 VRTREF_TRACE_LIVE(vrtref_trace_live_f32_f32, float, float)
 VRTREF_TRACE_LIVE(vrtref_trace_live_f32_i16, float, int16_t)
 VRTREF_TRACE_LIVE(vrtref_trace_live_i16_f32, diff_t, float)

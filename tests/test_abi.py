@@ -1,0 +1,60 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/vrt_b200.h declares, fails
+loudly (no fallback) without a CUDA device, and the product never touches oracle/."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vrt_b200.h")).read()
+    return sorted(set(re.findall(r"VRT_API\s+[\w\s\*]+?\b(vrt_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import volumeraytracer_b200 as vrt
+    from volumeraytracer_b200 import _lib
+    lib = vrt.lib()
+    declared = header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "libvrt_b200.so does not export %s" % name
+    assert sorted(_lib.SYMBOLS) == declared, "python binding list and header disagree"
+    assert b"sm_100a" in lib.vrt_version()
+
+
+def test_argument_validation_needs_no_gpu():
+    import volumeraytracer_b200 as vrt
+    from volumeraytracer_b200 import _lib
+    lib = vrt.lib()
+    h = C.c_void_p()
+    b = np.array([4, 4, 4, 4], dtype=np.uint64)
+    assert lib.vrt_scene_create(C.byref(h), 0, 4, b.ctypes.data_as(C.c_void_p), 0, None, None, 0) == _lib.VRT_ERR_INVALID
+    assert lib.vrt_trace(None, 0, None, None, 0, None, 0, 0, 0, None, None, None, None, None) == _lib.VRT_ERR_INVALID
+    assert b"scene is null" in lib.vrt_last_error()
+    assert lib.vrt_scene_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import volumeraytracer_b200 as vrt
+    planes = [np.zeros(64, np.float32)] * 3
+    with pytest.raises(vrt.VrtError):
+        vrt.TraceRaysCu([4, 4, 4], planes, np.zeros(64, np.uint32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "volumeraytracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert not re.search(r'#include\s*[<"].*vrt_oracle', src), f
+                assert "libvrt_oracle" not in src and "libvrt_ref" not in src, f

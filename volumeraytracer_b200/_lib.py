@@ -18,7 +18,7 @@ VRT_OPT_KERNEL, VRT_OPT_BLOCK_THREADS, VRT_OPT_REFILL, VRT_OPT_CHUNK_RAYS, VRT_O
 SYMBOLS = [
     "vrt_last_error", "vrt_version", "vrt_device_count", "vrt_scene_create", "vrt_scene_create_interleaved",
     "vrt_scene_create_device", "vrt_scene_create_from_ior", "vrt_scene_destroy", "vrt_scene_info",
-    "vrt_scene_download", "vrt_scene_set_option", "vrt_scene_get_option", "vrt_trace", "vrt_trace_device",
+    "vrt_scene_download", "vrt_scene_export_device", "vrt_scene_set_option", "vrt_scene_get_option", "vrt_trace", "vrt_trace_device",
     "vrt_normalise_rays_device", "vrt_measure_gather_bandwidth", "vrt_launch_count",
 ]
 
@@ -54,6 +54,7 @@ def lib():
         L.vrt_scene_destroy.argtypes = [vp]
         L.vrt_scene_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
         L.vrt_scene_download.argtypes = [vp, vp, vp]
+        L.vrt_scene_export_device.argtypes = [vp, vp, vp, vp]
         L.vrt_scene_set_option.argtypes = [vp, i32, C.c_int64]
         L.vrt_scene_get_option.argtypes = [vp, i32, C.POINTER(C.c_int64)]
         L.vrt_trace.argtypes = [vp, u64, vp, vp, i32, vp, u32, u32, C.c_uint, vp, vp, vp, vp, vp]

@@ -352,6 +352,16 @@ int vrt_scene_download(const vrt_scene *s, void *host_volume, uint32_t *host_tra
     return VRT_OK;
 }
 
+int vrt_scene_export_device(const vrt_scene *s, void *d_volume_out, uint32_t *d_translucency_out, void *cuda_stream)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d_volume_out) VRT_CUDA(cudaMemcpyAsync(d_volume_out, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
+    if (d_translucency_out && s->d_translucency) VRT_CUDA(cudaMemcpyAsync(d_translucency_out, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToDevice, st));
+    return VRT_OK;
+}
+
 int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
 {
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");

@@ -117,6 +117,14 @@ class TraceRaysCu:
         L.check(L.lib().vrt_scene_download(self._h, _p(vol), _p(tr)))
         return vol, tr
 
+    def export_device(self, volume_tensor, translucency_tensor=None, stream=None):
+        """D2D copy of the staged volume into torch CUDA tensors (the buffers an NCCL broadcast then replicates)."""
+        import torch
+        st = torch.cuda.current_stream(volume_tensor.device) if stream is None else stream
+        L.check(L.lib().vrt_scene_export_device(self._h, C.c_void_p(volume_tensor.data_ptr()),
+                                                C.c_void_p(translucency_tensor.data_ptr()) if translucency_tensor is not None else None,
+                                                C.c_void_p(st.cuda_stream)))
+
     def set_option(self, key, value):
         L.check(L.lib().vrt_scene_set_option(self._h, key, int(value)))
 

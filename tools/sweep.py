@@ -37,7 +37,14 @@ def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
     return res
 
 
-VARIANTS = [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (3, 256, 0, 8), (3, 64, 0, 8), (3, 128, 32, 8), (3, 128, 16, 8),
+def _env_variants():
+    v = os.environ.get("SWEEP_VARIANTS")
+    if not v:
+        return None
+    return [tuple(int(x) for x in item.split(",")) for item in v.split(";")]
+
+
+VARIANTS = _env_variants() or [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (3, 256, 0, 8), (3, 64, 0, 8), (3, 128, 32, 8), (3, 128, 16, 8),
             (3, 128, 8, 8), (3, 128, 1, 8), (3, 128, 16, 2), (3, 128, 16, 32), (3, 256, 16, 8), (2, 128, 16, 8), (1, 128, 16, 8)]
 
 

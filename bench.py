@@ -205,6 +205,7 @@ def run_ours(args, rank, local_rank, world):
     import volumeraytracer_b200 as vrt
     from volumeraytracer_b200 import workloads as W
     import torch.distributed as dist
+    from volumeraytracer_b200 import dist as vd
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -230,7 +231,7 @@ def run_ours(args, rank, local_rank, world):
             scene0.export_device(vol_t)
         torch.cuda.synchronize()
         tb = time.time()
-        dist.broadcast(vol_t, src=0)
+        vd.broadcast_volume(vol_t, src=0)                     # ONE collective, at scene creation (NCCL over NVLink)
         torch.cuda.synchronize()
         bcast_s = time.time() - tb
         scene = vrt.TraceRaysCu.from_device([size - 2] * 3, vol_t, None, borrow=True)

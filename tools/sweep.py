@@ -41,7 +41,7 @@ def _env_variants():
     v = os.environ.get("SWEEP_VARIANTS")
     if not v:
         return None
-    return [tuple(int(x) for x in item.split(",")) for item in v.split(";")]
+    return [tuple(int(x) for x in item.split(",")) for item in v.replace(";", ":").split(":")]
 
 
 VARIANTS = _env_variants() or [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (3, 256, 0, 8), (3, 64, 0, 8), (3, 128, 32, 8), (3, 128, 16, 8),

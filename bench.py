@@ -159,7 +159,7 @@ def run_reference_arm(args, rank, world):
     window = 512 if args.ref_window is None else args.ref_window            # 512^2 = 262 144 rays x 2048 steps per bench step
     vol, ob, pos, d = c5_sample_on_cpu(window)
     use_ref = ref.available()
-    threads = ref.omp_max_threads() if use_ref else (os.cpu_count() or 1)
+    threads = len(os.sched_getaffinity(0))      # explicit: torchrun sets OMP_NUM_THREADS=1, the harness passes num_threads itself
 
     def one_pass():
         if use_ref:
@@ -386,7 +386,7 @@ def cpu_baseline_and_parity(scene, pos_t, dir_t, epos, edir, eit, side, iters):
     # (a) cpu baseline, 1/16 subsample (every 4th ray in y and z): same volume, same coverage of it as the full batch
     p_c = np.ascontiguousarray(P[::4, ::4].reshape(-1, 3)); d_c = np.ascontiguousarray(D[::4, ::4].reshape(-1, 3))
     use_ref = ref.available()
-    threads = ref.omp_max_threads() if use_ref else (os.cpu_count() or 1)
+    threads = len(os.sched_getaffinity(0))
     with quiet_stdout():
         t0 = time.perf_counter()
         if use_ref:

@@ -57,7 +57,11 @@ enum {
 /* vrt_scene_create* flags */
 enum {
     VRT_SCENE_DEFAULT = 0,
-    VRT_SCENE_BORROW  = 1u << 0  /* vrt_scene_create_device: use the caller's device buffers in place (no copy, not freed) */
+    VRT_SCENE_BORROW  = 1u << 0, /* vrt_scene_create_device: use the caller's device buffers in place (no copy, not freed) */
+    /* layout study: store the volume as 2x2x2-voxel bricks (one 128-byte line per brick for a float scene) instead of the
+     * reference's linear interleaved order.  3-D only, no path output; results are bit-identical, only the memory
+     * behaviour changes (fewer, fuller lines per cell: helps incoherent ray batches).  Not with VRT_SCENE_BORROW. */
+    VRT_SCENE_LAYOUT_BRICK = 1u << 1
 };
 
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */
@@ -66,7 +70,9 @@ enum {
     VRT_OPT_BLOCK_THREADS = 1,  /* 64..512, multiple of 32 */
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
-    VRT_OPT_STEPS_PER_POLL= 4   /* marching steps between two refill polls */
+    VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
+    VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an
+                                   incoherent batch's working set inside L1/L2 */
 };
 
 VRT_API const char *vrt_last_error(void);

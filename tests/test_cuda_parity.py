@@ -332,3 +332,111 @@ def test_dropin_behind_the_reference_cpp_api(vrt, oracle, kind):
     p2, d2 = oracle.normalise(shape, ior, pos, d)
     want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 300, round_mode=oracle.ROUND_DEVICE)
     assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the five BASELINE.json configurations at sizes the CPU oracle finishes in seconds (bench.py runs config 5 at full size)
+
+def _run_config(vrt, oracle, ior, tr, pos, d, iterations, live=False, minb=0):
+    shape = ior.shape
+    sc = vrt.RaytraceScene(shape, ior, tr)
+    got = sc.trace_rays(pos, d, [1, 1, 1], minb, iterations, live_translucency=live)
+    vol, trc = sc._calculation_object.download_volume()
+    ob = sc._calculation_object._output_sizes
+    p2, d2 = oracle.normalise(shape, ior, pos, d)
+    want = oracle.trace(vol, ob, p2, d2, [1, 1, 1], iterations, translucency=trc if live else None, min_brightness=minb,
+                        round_mode=oracle.ROUND_DEVICE)
+    assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2]) and EQ(got[3], want[3])
+    # and the oracle's own scene prep agrees with the GPU's
+    ob2, _, planes, trc2 = oracle.prep(shape, ior, tr)
+    assert EQ(oracle.fold(planes, trc2), vol) and EQ(trc2, trc)
+    sc.close()
+    return got, p2
+
+
+def test_config2_luneburg_lens(vrt, oracle):
+    """config 2 geometry at 64^3: parallel +x rays through a Luneburg-style GRIN lens focus on the far side."""
+    from volumeraytracer_b200 import workloads as W
+    size, R = 64, 25.0
+    ior = W.ior_luneburg(size, R)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    pos, d = W.rays_parallel_x(96, 96, 8.0, 55.0, x0=2.0)
+    got, _ = _run_config(vrt, oracle, ior, tr, pos, d, 1024)
+    # physics sanity: rays that entered the lens cross the axis near the rim focus (x = c + R, y = z = c)
+    c = (size - 1) / 2.0
+    y0 = pos[:, 1] / 65536.0 - c; z0 = pos[:, 2] / 65536.0 - c
+    inside = y0 ** 2 + z0 ** 2 < (0.6 * R) ** 2
+    e = got[0][inside] / 65536.0; dd = got[1][inside].astype(np.float64)
+    # intersect the exit ray with the plane x = c + R, going backwards along the final direction
+    t = (c + R - e[:, 0]) / dd[:, 0]
+    yf = e[:, 1] + t * dd[:, 1] - c; zf = e[:, 2] + t * dd[:, 2] - c
+    assert np.median(np.hypot(yf, zf)) < 1.5, np.median(np.hypot(yf, zf))
+
+
+def test_config3_translucency_and_min_brightness(vrt, oracle):
+    """config 3 at 96^3: live translucency plane + opaque ball + min_brightness: all three exit classes occur."""
+    from volumeraytracer_b200 import workloads as W
+    size = 96
+    ior = W.ior_sines(size, period=32.0)
+    tr = W.translucency_c3(size)
+    absorb = (np.uint64(0xFFFFFFFF) - tr.astype(np.uint64)) * np.uint64(8)          # rescale absorption to the shorter paths
+    tr2 = (np.uint64(0xFFFFFFFF) - np.minimum(absorb, np.uint64(0xFFFFFFFF))).astype(np.uint32)
+    tr2[tr == 0] = 0
+    pos, d = W.rays_parallel_x(128, 128, 4.0, size - 5.0, x0=2.0)
+    minb = 0x40000000
+    got, _ = _run_config(vrt, oracle, ior, tr2, pos, d, 4096, live=True, minb=minb)
+    eit, light = got[2], got[3]
+    escaped = light >= minb
+    dimmed = light < minb
+    assert escaped.sum() > 100 and dimmed.sum() > 100
+    # rays aimed at the opaque ball stop early with light still above the threshold
+    stopped_opaque = escaped & (eit < np.percentile(eit[escaped], 5))
+    assert stopped_opaque.sum() > 10
+    assert len(np.unique(eit)) > 50
+
+
+def test_config4_harmonic_field_random_rays(vrt, oracle):
+    from volumeraytracer_b200 import workloads as W
+    size = 64
+    ior = W.solve_harmonic(size, inner_radius=8.0, sweeps=60)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    pos, d = W.rays_random(30000, 8.0, size - 9.0, 0x5EED0004)
+    got, _ = _run_config(vrt, oracle, ior, tr, pos, d, 4096)
+    assert got[2].min() >= 2 and got[2].max() < 4096 and len(np.unique(got[2])) > 100
+
+
+def test_config5_roofline_workload_small(vrt, oracle):
+    """config 5 at 128^3 / cap 256: every ray runs the cap, so the reported steps are exactly rays x cap."""
+    from volumeraytracer_b200 import workloads as W
+    size = 128
+    ior = W.ior_c5(size, period=32.0)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    pos, d = W.rays_parallel_x(256, 256, 2.0, size - 3.0, x0=2.0)
+    got, _ = _run_config(vrt, oracle, ior, tr, pos, d, 256)
+    inner = (pos[:, 1] > 0x80000) & (pos[:, 1] < (size - 8) << 16) & (pos[:, 2] > 0x80000) & (pos[:, 2] < (size - 8) << 16)
+    assert np.all(got[2][inner] == 256)
+
+
+@pytest.mark.parametrize("volk", ["f32", "i16"])
+@pytest.mark.parametrize("live", [False, True])
+def test_bricked_layout_is_bit_identical(vrt, oracle, volk, live):
+    """VRT_SCENE_LAYOUT_BRICK (2x2x2-voxel bricks) changes only where bytes live, never a result; odd extents are padded."""
+    shape = (31, 36, 29)
+    ior, tr = S.random_scene(shape, seed=19, kind="f32" if volk == "f32" else "u32", opaque_fraction=0.004)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    if live:
+        trc = trc.copy(); trc[trc != 0] -= np.uint32(1 << 24)
+    vol = oracle.fold(planes, trc)
+    pos, d = S.random_rays(ob, 8000, seed=3, dir_kind="f32" if volk == "f32" else "i16", scale=1.2)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.25, 0.8], 300, translucency=trc if live else None, min_brightness=0x40000000,
+                        round_mode=oracle.ROUND_DEVICE)
+    t = vrt.TraceRaysCu(ob, planes, trc, bricked=True)
+    for refill in (0, 1, 32):
+        t.set_option(vrt.VRT_OPT_REFILL, refill)
+        got = t.trace_rays_cu(pos, d, [1.0, 1.25, 0.8], 0x40000000, 300, live_translucency=live)
+        _assert_same(got, want[:4], "bricked refill=%d" % refill)
+    back, back_tr = t.download_volume()                 # handed out in the reference's linear order
+    assert EQ(back, vol) and EQ(back_tr, trc)
+    with pytest.raises(vrt.VrtError):
+        t.trace_rays_cu(pos, d, [1, 1, 1], 0, 300, trace_paths=True)

@@ -13,6 +13,7 @@ import volumeraytracer_b200 as vrt
 from volumeraytracer_b200 import workloads as W
 
 dev = torch.device("cuda", 0)
+BRICK = bool(int(os.environ.get("SWEEP_BRICK", "0")))
 
 
 def timed(fn, reps=2):
@@ -26,12 +27,15 @@ def timed(fn, reps=2):
 
 def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
     res = []
-    for kver, block, refill, poll in variants:
+    for var in variants:
+        kver, block, refill, poll = var[:4]
+        ctas = var[4] if len(var) > 4 else 0
         co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)
         co.set_option(vrt.VRT_OPT_REFILL, refill); co.set_option(vrt.VRT_OPT_STEPS_PER_POLL, poll)
+        co.set_option(vrt.VRT_OPT_MAX_CTAS_PER_SM, ctas)
         t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
         steps = int(out[2].to(torch.int64).sum().item())
-        print(json.dumps(dict(cfg=name, kver=kver, block=block, refill=refill, poll=poll, sec=round(t, 4), steps=steps,
+        print(json.dumps(dict(cfg=name + ("_brick" if BRICK else ""), kver=kver, block=block, refill=refill, poll=poll, ctas=ctas, sec=round(t, 4), steps=steps,
                               grays=round(steps / t / 1e9, 2))), flush=True)
         res.append((steps / t / 1e9, kver, block, refill, poll))
     return res
@@ -50,7 +54,7 @@ VARIANTS = _env_variants() or [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (
 
 def cfg_c5(size=1024, nray=4096, iterations=2048):
     ior = W.ior_c5_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
-    t0 = time.time(); sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    t0 = time.time(); sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK); torch.cuda.synchronize()
     print("c5 scene prep %.2fs, volume %.2f GB" % (time.time() - t0, sc.volume_bytes / 1e9), flush=True)
     del tr
     pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
@@ -63,7 +67,7 @@ def cfg_c5(size=1024, nray=4096, iterations=2048):
 def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
     ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
     tr = W.clear_translucency_torch((size,) * 3, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK); torch.cuda.synchronize()
     pos, d = W.rays_random(nrays, 8.0, size - 9.0, 0x5EED0004)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
@@ -73,7 +77,7 @@ def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
 
 def cfg_c3(size=512, nray=2048, iterations=4096):
     ior = W.ior_sines_torch(size, dev); tr = W.translucency_c3_torch(size, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK); torch.cuda.synchronize()
     pos, d = W.rays_parallel_x(nray, nray, 4.0, size - 5.0, x0=2.0)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
@@ -83,7 +87,7 @@ def cfg_c3(size=512, nray=2048, iterations=4096):
 
 def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=True):
     ior = W.ior_luneburg_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK); torch.cuda.synchronize()
     pos, d = W.rays_parallel_x(nray, nray, 30.0, 225.0, x0=2.0)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)

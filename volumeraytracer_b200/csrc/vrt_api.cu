@@ -73,6 +73,8 @@ struct vrt_scene
     void     *d_volume = nullptr;
     uint32_t *d_translucency = nullptr;
     bool      owns = true;
+    bool      bricked = false;     // VRT_SCENE_LAYOUT_BRICK
+    uint64_t  nb[3] = {1, 1, 1};   // bricks per axis
     // kept only by vrt_scene_create_from_ior, for vrt_normalise_rays_device (f2)
     void     *d_ior = nullptr;
     int       ior_dtype = VRT_F32;
@@ -80,7 +82,7 @@ struct vrt_scene
     bool      owns_ior = false;
     int       num_sms = 148;
     // options
-    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{32};
+    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{32}, opt_max_ctas{0};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -128,6 +130,41 @@ static int alloc_scene_buffers(vrt_scene *s)
     return VRT_OK;
 }
 
+// re-stage a freshly created (linear) scene as 2x2x2 bricks; dir = 1 linear -> brick into a new buffer
+static int convert_layout(const vrt_scene *s, const void *src, void *dst, int to_brick, cudaStream_t st)
+{
+    const unsigned long long nslots = s->nb[0] * s->nb[1] * s->nb[2] * 8ull;
+    const unsigned grid = (unsigned)((nslots + 255) / 256);
+    if (s->dtype == VRT_F32)
+        brick_convert_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, (uint32_t)s->bounds[0], (uint32_t)s->bounds[1], (uint32_t)s->bounds[2],
+                                                          (uint32_t)s->nb[1], (uint32_t)s->nb[2], nslots, to_brick);
+    else
+        brick_convert_kernel<int2><<<grid, 256, 0, st>>>((const int2 *)src, (int2 *)dst, (uint32_t)s->bounds[0], (uint32_t)s->bounds[1], (uint32_t)s->bounds[2],
+                                                        (uint32_t)s->nb[1], (uint32_t)s->nb[2], nslots, to_brick);
+    ++g_launches;
+    VRT_CUDA(cudaGetLastError());
+    return VRT_OK;
+}
+
+static int apply_layout_flag(vrt_scene *s, unsigned flags)
+{
+    if (!(flags & VRT_SCENE_LAYOUT_BRICK)) return VRT_OK;
+    if (s->dim != 3) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK is 3-D only");
+    if (!s->owns) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK cannot be combined with VRT_SCENE_BORROW");
+    for (int d = 0; d < 3; ++d) s->nb[d] = (s->bounds[d] + 1) / 2;
+    const unsigned long long nslots = s->nb[0] * s->nb[1] * s->nb[2] * 8ull;
+    if (nslots >= (1ull << 32)) return fail(VRT_ERR_INVALID, "bricked volume has >= 2^32 voxel slots");
+    void *dst = nullptr;
+    VRT_CUDA(cudaMalloc(&dst, nslots * 4 * elem_size(s->dtype)));
+    int rc = convert_layout(s, s->d_volume, dst, 1, nullptr);
+    if (rc == VRT_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) rc = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { cudaFree(dst); return rc; }
+    cudaFree(s->d_volume);
+    s->d_volume = dst;
+    s->bricked = true;
+    return VRT_OK;
+}
+
 extern "C" {
 
 const char *vrt_last_error(void) { return g_last_error.c_str(); }
@@ -156,7 +193,6 @@ int vrt_scene_destroy(vrt_scene *s)
 int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
                      const void *const *diff_planes, const uint32_t *translucency_cropped, unsigned flags)
 {
-    (void)flags;
     if (!diff_planes || !translucency_cropped) return fail(VRT_ERR_INVALID, "null input");
     for (int d = 0; d < dim && d < 3; ++d) if (!diff_planes[d]) return fail(VRT_ERR_INVALID, "null diff plane");
     vrt_scene *s = nullptr;
@@ -186,6 +222,8 @@ int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bound
     }
     cudaFree(tmp);
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    rc = apply_layout_flag(s, flags);
+    if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
 }
@@ -193,7 +231,6 @@ int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bound
 int vrt_scene_create_interleaved(vrt_scene **out, int device, int dim, const uint64_t *bounds, int diff_dtype,
                                  const void *volume_interleaved, const uint32_t *translucency_cropped, unsigned flags)
 {
-    (void)flags;
     if (!volume_interleaved || !translucency_cropped) return fail(VRT_ERR_INVALID, "null input");
     vrt_scene *s = nullptr;
     int rc = new_scene(&s, device, dim, bounds, diff_dtype);
@@ -204,6 +241,8 @@ int vrt_scene_create_interleaved(vrt_scene **out, int device, int dim, const uin
     cudaError_t e = cudaMemcpy(s->d_volume, volume_interleaved, s->nvox * (dim + 1) * elem_size(diff_dtype), cudaMemcpyHostToDevice);
     e = e == cudaSuccess ? cudaMemcpy(s->d_translucency, translucency_cropped, s->nvox * 4, cudaMemcpyHostToDevice) : e;
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+    rc = apply_layout_flag(s, flags);
+    if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
 }
@@ -233,6 +272,8 @@ int vrt_scene_create_device(vrt_scene **out, int device, int dim, const uint64_t
             e = e == cudaSuccess ? cudaMemset(s->d_translucency, 0xFF, s->nvox * 4) : e;
         if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
     }
+    rc = apply_layout_flag(s, flags);
+    if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
 }
@@ -264,7 +305,6 @@ static void make_stamp(int dim, int ax, const uint64_t *ib, Stamp *st)
 int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64_t *bounds, int ior_dtype,
                               const void *ior, const uint32_t *translucency, int ptrs_on_device, unsigned flags)
 {
-    (void)flags;
     if (!ior || !translucency || !bounds) return fail(VRT_ERR_INVALID, "null input");
     if (ior_dtype != VRT_F32 && ior_dtype != VRT_U32) return fail(VRT_ERR_INVALID, "ior_dtype must be VRT_F32 or VRT_U32");
     if (dim != 2 && dim != 3) return fail(VRT_ERR_INVALID, "Illegal dimension: " + std::to_string(dim));   // image_util.cpp:558
@@ -325,6 +365,8 @@ int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); }
     if (flags_h[0]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "refraction-index underflow"); }   // image_util.cpp:536-541,607-610
     if (flags_h[1]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "differention overflow"); }        // image_util.cpp:293-296
+    rc = apply_layout_flag(s, flags);
+    if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
 }
@@ -347,7 +389,17 @@ int vrt_scene_download(const vrt_scene *s, void *host_volume, uint32_t *host_tra
 {
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     DeviceGuard g(s->device);
-    if (host_volume) VRT_CUDA(cudaMemcpy(host_volume, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToHost));
+    if (host_volume && s->bricked)      // hand out the reference's linear layout
+    {
+        void *tmp = nullptr;
+        VRT_CUDA(cudaMalloc(&tmp, s->nvox * 4 * elem_size(s->dtype)));
+        int rc = convert_layout(s, s->d_volume, tmp, 0, nullptr);
+        cudaError_t e = rc == VRT_OK ? cudaMemcpy(host_volume, tmp, s->nvox * 4 * elem_size(s->dtype), cudaMemcpyDeviceToHost) : cudaSuccess;
+        cudaFree(tmp);
+        if (rc) return rc;
+        VRT_CUDA(e);
+    }
+    else if (host_volume) VRT_CUDA(cudaMemcpy(host_volume, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToHost));
     if (host_translucency && s->d_translucency) VRT_CUDA(cudaMemcpy(host_translucency, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToHost));
     return VRT_OK;
 }
@@ -357,7 +409,8 @@ int vrt_scene_export_device(const vrt_scene *s, void *d_volume_out, uint32_t *d_
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (d_volume_out) VRT_CUDA(cudaMemcpyAsync(d_volume_out, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
+    if (d_volume_out && s->bricked) { int rc = convert_layout(s, s->d_volume, d_volume_out, 0, st); if (rc) return rc; }
+    else if (d_volume_out) VRT_CUDA(cudaMemcpyAsync(d_volume_out, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
     if (d_translucency_out && s->d_translucency) VRT_CUDA(cudaMemcpyAsync(d_translucency_out, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToDevice, st));
     return VRT_OK;
 }
@@ -372,6 +425,7 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_REFILL:         if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "refill threshold must be 0..32"); s->opt_refill = v; break;
     case VRT_OPT_CHUNK_RAYS:     if (v < 0) return fail(VRT_ERR_INVALID, "chunk must be >= 0"); s->opt_chunk = v; break;
     case VRT_OPT_STEPS_PER_POLL: if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "steps per poll must be 1..4096"); s->opt_poll = v; break;
+    case VRT_OPT_MAX_CTAS_PER_SM: if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "max CTAs per SM must be 0..32"); s->opt_max_ctas = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -387,6 +441,7 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_REFILL: *v = s->opt_refill; break;
     case VRT_OPT_CHUNK_RAYS: *v = s->opt_chunk; break;
     case VRT_OPT_STEPS_PER_POLL: *v = s->opt_poll; break;
+    case VRT_OPT_MAX_CTAS_PER_SM: *v = s->opt_max_ctas; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -401,6 +456,8 @@ template <typename VoxT, bool DIR_I16, bool LIVE, bool PATH, int KVER>
 static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, cudaStream_t st)
 {
     auto kern = march3_kernel<VoxT, DIR_I16, LIVE, PATH, KVER>;
+    static std::atomic<bool> carved{false};     // the marcher uses no shared memory: give the whole unified array to L1
+    if (!carved.exchange(true)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     unsigned grid;
     if (p.refill == 0) grid = (unsigned)((p.n + block - 1) / block);
     else
@@ -409,6 +466,8 @@ static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, 
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
+        const int cap = (int)s->opt_max_ctas.load();
+        if (cap > 0 && cap < per_sm) per_sm = cap;
         const unsigned long long want = (p.n + block - 1) / block;
         grid = (unsigned)std::min<unsigned long long>((unsigned long long)per_sm * s->num_sms, want);
     }
@@ -425,6 +484,7 @@ static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path
     {
     case 1: return launch3<VoxT, DIR_I16, LIVE, false, 1>(s, p, block, st);
     case 2: return launch3<VoxT, DIR_I16, LIVE, false, 2>(s, p, block, st);
+    case 4: return launch3<VoxT, DIR_I16, LIVE, false, 4>(s, p, block, st);
     default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
     }
 }
@@ -461,6 +521,7 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     if ((flags & VRT_TRACE_PATHS) && n && !path) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs a path buffer");
     if ((flags & VRT_TRACE_PATHS) && iterations == 0) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs iterations >= 1");
     if ((flags & VRT_TRACE_LIVE_TRANSLUCENCY) && !s->d_translucency) return fail(VRT_ERR_INVALID, "scene has no translucency plane");
+    if ((flags & VRT_TRACE_PATHS) && s->bricked) return fail(VRT_ERR_UNSUPPORTED, "path output is not implemented for VRT_SCENE_LAYOUT_BRICK scenes");
     if (n >= (1ull << 40)) return fail(VRT_ERR_INVALID, "too many rays");
     return VRT_OK;
 }
@@ -483,6 +544,8 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.counter = counter;
     int kver = (int)s->opt_kernel.load();
     if (kver == 0) kver = 3;
+    if (s->bricked) kver = 4;
+    p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvrt_b200.so")
+LIB_PATH = os.environ.get("VRT_B200_LIB") or os.path.join(_HERE, "libvrt_b200.so")   # override only for tuning experiments
 
 VRT_OK, VRT_ERR_INVALID, VRT_ERR_CUDA, VRT_ERR_NOMEM, VRT_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 VRT_F32, VRT_I16, VRT_U32 = 0, 1, 2

@@ -61,7 +61,11 @@ enum {
     /* layout study: store the volume as 2x2x2-voxel bricks (one 128-byte line per brick for a float scene) instead of the
      * reference's linear interleaved order.  3-D only, no path output; results are bit-identical, only the memory
      * behaviour changes (fewer, fuller lines per cell: helps incoherent ray batches).  Not with VRT_SCENE_BORROW. */
-    VRT_SCENE_LAYOUT_BRICK = 1u << 1
+    VRT_SCENE_LAYOUT_BRICK = 1u << 1,
+    /* By default the device copy of an int16 (diff_t) 3-D scene is widened to float when it fits (<= 24 GiB): the marcher
+     * converts int16 to float before its first multiply anyway (cu:164), so results are bit-identical while the conversions
+     * leave the hot loop (+37 % on coherent bundles, at twice the device memory).  This flag keeps the 8-byte voxels. */
+    VRT_SCENE_KEEP_I16 = 1u << 2
 };
 
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */

@@ -431,7 +431,7 @@ def test_bricked_layout_is_bit_identical(vrt, oracle, volk, live):
     pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
     want = oracle.trace(vol, ob, pos, d, [1.0, 1.25, 0.8], 300, translucency=trc if live else None, min_brightness=0x40000000,
                         round_mode=oracle.ROUND_DEVICE)
-    t = vrt.TraceRaysCu(ob, planes, trc, bricked=True)
+    t = vrt.TraceRaysCu(ob, planes, trc, bricked=True, keep_i16=live)     # covers widened-float and kept-int16 staging
     for refill in (0, 1, 32):
         t.set_option(vrt.VRT_OPT_REFILL, refill)
         got = t.trace_rays_cu(pos, d, [1.0, 1.25, 0.8], 0x40000000, 300, live_translucency=live)
@@ -440,3 +440,72 @@ def test_bricked_layout_is_bit_identical(vrt, oracle, volk, live):
     assert EQ(back, vol) and EQ(back_tr, trc)
     with pytest.raises(vrt.VrtError):
         t.trace_rays_cu(pos, d, [1, 1, 1], 0, 300, trace_paths=True)
+
+
+def test_c_abi_in_place_and_concurrent_host_threads(vrt, oracle):
+    """The boundary contract: results may be written back into the start buffers (java_binding.cpp:158-160), and one scene
+    may be traced from several host threads at once (the JNI binding can be entered from any Java thread)."""
+    import ctypes as C
+    import threading
+    from volumeraytracer_b200 import _lib
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (36, 30, 33), 4, "f32")
+    lib = vrt.lib()
+    isc = np.array([1, 1, 1], np.float32)
+    results = {}
+
+    def worker(k):
+        pos, d = S.random_rays(ob, 20000 + 13 * k, seed=100 + k)
+        pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+        want = oracle.trace(vol, ob, pos, d, [1, 1, 1], 300, round_mode=oracle.ROUND_DEVICE, threads=2)
+        p = pos.copy(); dd = d.copy()
+        n = p.shape[0]
+        eit = np.empty(n, np.uint32); light = np.empty(n, np.uint32)
+        ok = True
+        for _ in range(3):
+            p[:] = pos; dd[:] = d
+            rc = lib.vrt_trace(t._h, n, p.ctypes.data, dd.ctypes.data, _lib.VRT_F32, isc.ctypes.data, 0, 300, 0,
+                               p.ctypes.data, dd.ctypes.data, eit.ctypes.data, light.ctypes.data, None)     # in place
+            ok = ok and rc == 0 and EQ(p, want[0]) and EQ(dd, want[1]) and EQ(eit, want[2])
+        results[k] = ok
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert results == {0: True, 1: True, 2: True, 3: True}
+
+
+def test_int16_scene_large_batch_matches_reference_cuda(vrt, oracle):
+    """int16 scene / int16 directions (the reference's default instantiation) on a 1M-ray batch: bit-exact against the
+    reference's own CUDA kernel, which also checks our whole-batch launch against its 32 768-ray chunking."""
+    from oracle import ref
+    if not ref.available(cuda=True):
+        pytest.skip("oracle/_ref/libvrt_ref_cuda.so not built")
+    from volumeraytracer_b200 import workloads as W
+    size = 96
+    ior = W.ior_to_u32(W.ior_luneburg(size, 36.0))
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    ob, iorlog, planes, trc = oracle.prep(ior.shape, ior, tr)
+    pos, d = W.rays_parallel_x(1024, 1024, 6.0, size - 7.0, x0=2.0)
+    pos, d = oracle.normalise(ior.shape, ior, pos, W.dirs_to_i16(d))
+    rt = ref.RefTracer(ob, planes, trc, cuda=True)
+    want = rt.trace(pos, d, [1, 1, 1], 0, 2048)
+    t = vrt.TraceRaysCu(ob, planes, trc)
+    got = t.trace_rays_cu(pos, d, [1, 1, 1], 0, 2048)
+    _assert_same(got, want[:4], "1M rays int16")
+    rt.close()
+
+
+def test_int16_scene_staging_variants_agree(vrt, oracle):
+    """An int16 scene is staged as float on the device by default (VRT_SCENE_KEEP_I16 keeps 8-byte voxels): same bits out,
+    and the volume is handed back as int16 either way."""
+    ob, planes, trc, vol, t_wide = _mk(vrt, oracle, (30, 34, 28), 9, "i16", opaque=0.004)
+    t_keep = vrt.TraceRaysCu(ob, planes, trc, keep_i16=True)
+    pos, d = S.random_rays(ob, 6000, seed=3, dir_kind="i16", scale=1.2)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1, 1, 1], 300, trace_path=True, round_mode=oracle.ROUND_DEVICE)
+    for t in (t_wide, t_keep):
+        _assert_same(t.trace_rays_cu(pos, d, [1, 1, 1], 0, 300, trace_paths=True), want, "staging")
+        back, _ = t.download_volume()
+        assert back.dtype == np.int16 and EQ(back, vol)

@@ -14,6 +14,7 @@ from volumeraytracer_b200 import workloads as W
 
 dev = torch.device("cuda", 0)
 BRICK = bool(int(os.environ.get("SWEEP_BRICK", "0")))
+KEEP16 = bool(int(os.environ.get("SWEEP_KEEP_I16", "0")))
 
 
 def timed(fn, reps=2):
@@ -61,6 +62,23 @@ def cfg_c5(size=1024, nray=4096, iterations=2048):
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
     run_variants("c5_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    sc.close()
+
+
+def cfg_c5i(size=1024, nray=4096, iterations=2048):
+    """config 5 with the int16 scene / int16 directions instantiation (64 B per ray-step, 8.5 GB volume)"""
+    ior = W.ior_c5_torch(size, dev)
+    ior_u = torch.floor(ior.double() * 65536.0 + 0.5).to(torch.int64)
+    ior_u = torch.where(ior_u >= (1 << 31), ior_u - (1 << 32), ior_u).to(torch.int32)
+    del ior
+    tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior_u, tr, bricked=BRICK, keep_i16=KEEP16); torch.cuda.synchronize()
+    print("c5 int16 scene, volume %.2f GB" % (sc.volume_bytes / 1e9), flush=True)
+    del tr
+    pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(W.dirs_to_i16(d).reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c5i_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
     sc.close()
 
 
@@ -126,4 +144,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c5": cfg_c5, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2}[w]()
+        {"c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2}[w]()

@@ -69,7 +69,8 @@ struct vrt_scene
     int       dim = 3;
     uint64_t  bounds[3] = {1, 1, 1};   // cropped (gradient volume) extents
     uint64_t  nvox = 0;
-    int       dtype = VRT_F32;
+    int       dtype = VRT_F32;     // element type at the API (the reference's DiffType)
+    int       store = VRT_F32;     // element type of the device copy (an int16 scene may be staged as float, see apply_storage)
     void     *d_volume = nullptr;
     uint32_t *d_translucency = nullptr;
     bool      owns = true;
@@ -114,7 +115,7 @@ static int new_scene(vrt_scene **out, int device, int dim, const uint64_t *bound
     VRT_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(VRT_ERR_INVALID, "no such CUDA device");
     vrt_scene *s = new vrt_scene();
-    s->device = device; s->dim = dim; s->dtype = dtype; s->nvox = nvox;
+    s->device = device; s->dim = dim; s->dtype = dtype; s->store = dtype; s->nvox = nvox;
     for (int d = 0; d < dim; ++d) s->bounds[d] = bounds[d];
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
@@ -130,12 +131,30 @@ static int alloc_scene_buffers(vrt_scene *s)
     return VRT_OK;
 }
 
-// re-stage a freshly created (linear) scene as 2x2x2 bricks; dir = 1 linear -> brick into a new buffer
-static int convert_layout(const vrt_scene *s, const void *src, void *dst, int to_brick, cudaStream_t st)
+// ---- staging: how the device copy of the volume is stored -------------------------------------------------------
+// Every creator first builds the reference's layout (linear interleaved, API element type).  apply_storage() then
+//   * widens an int16 scene to float on the device (exact: the marcher converts int16 -> float before its first
+//     multiply anyway, cu:164/176), which takes the conversions out of the cell reload: +37 % on coherent bundles at
+//     twice the memory; skipped with VRT_SCENE_KEEP_I16, for borrowed buffers, for 2-D and above 24 GiB;
+//   * re-orders it into 2x2x2 bricks when VRT_SCENE_LAYOUT_BRICK is set.
+// linearise() is the inverse, used by vrt_scene_download / vrt_scene_export_device.
+
+__global__ void widen_i16_kernel(const short *in, float *out, unsigned long long n)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void narrow_f32_kernel(const float *in, short *out, unsigned long long n)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (short)__float2int_rn(in[i]);
+}
+
+static int brick_convert(const vrt_scene *s, const void *src, void *dst, int to_brick, cudaStream_t st)
 {
     const unsigned long long nslots = s->nb[0] * s->nb[1] * s->nb[2] * 8ull;
     const unsigned grid = (unsigned)((nslots + 255) / 256);
-    if (s->dtype == VRT_F32)
+    if (s->store == VRT_F32)
         brick_convert_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, (uint32_t)s->bounds[0], (uint32_t)s->bounds[1], (uint32_t)s->bounds[2],
                                                           (uint32_t)s->nb[1], (uint32_t)s->nb[2], nslots, to_brick);
     else
@@ -146,8 +165,25 @@ static int convert_layout(const vrt_scene *s, const void *src, void *dst, int to
     return VRT_OK;
 }
 
-static int apply_layout_flag(vrt_scene *s, unsigned flags)
+static int apply_storage(vrt_scene *s, unsigned flags)
 {
+    const unsigned long long nelem = s->nvox * (unsigned long long)(s->dim + 1);
+    if (s->owns && s->dtype == VRT_I16 && s->dim == 3 && !(flags & VRT_SCENE_KEEP_I16) && nelem * 4ull <= (24ull << 30))
+    {
+        void *wide = nullptr;
+        if (cudaMalloc(&wide, nelem * 4) == cudaSuccess)
+        {
+            widen_i16_kernel<<<(unsigned)((nelem + 255) / 256), 256>>>((const short *)s->d_volume, (float *)wide, nelem);
+            ++g_launches;
+            cudaError_t e = cudaGetLastError();
+            e = e == cudaSuccess ? cudaDeviceSynchronize() : e;
+            if (e != cudaSuccess) { cudaFree(wide); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+            cudaFree(s->d_volume);
+            s->d_volume = wide;
+            s->store = VRT_F32;
+        }
+        else cudaGetLastError();       // not enough memory for the wide copy: keep int16
+    }
     if (!(flags & VRT_SCENE_LAYOUT_BRICK)) return VRT_OK;
     if (s->dim != 3) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK is 3-D only");
     if (!s->owns) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK cannot be combined with VRT_SCENE_BORROW");
@@ -155,13 +191,44 @@ static int apply_layout_flag(vrt_scene *s, unsigned flags)
     const unsigned long long nslots = s->nb[0] * s->nb[1] * s->nb[2] * 8ull;
     if (nslots >= (1ull << 32)) return fail(VRT_ERR_INVALID, "bricked volume has >= 2^32 voxel slots");
     void *dst = nullptr;
-    VRT_CUDA(cudaMalloc(&dst, nslots * 4 * elem_size(s->dtype)));
-    int rc = convert_layout(s, s->d_volume, dst, 1, nullptr);
+    VRT_CUDA(cudaMalloc(&dst, nslots * 4 * elem_size(s->store)));
+    int rc = brick_convert(s, s->d_volume, dst, 1, nullptr);
     if (rc == VRT_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) rc = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
     if (rc) { cudaFree(dst); return rc; }
     cudaFree(s->d_volume);
     s->d_volume = dst;
     s->bricked = true;
+    return VRT_OK;
+}
+
+// write the volume in the reference's layout and API element type into d_out (device memory, nvox*(dim+1) elements)
+static int linearise(const vrt_scene *s, void *d_out, cudaStream_t st)
+{
+    const unsigned long long nelem = s->nvox * (unsigned long long)(s->dim + 1);
+    const bool narrow = s->store != s->dtype;
+    if (!s->bricked && !narrow)
+    {
+        VRT_CUDA(cudaMemcpyAsync(d_out, s->d_volume, nelem * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
+        return VRT_OK;
+    }
+    const void *lin = s->d_volume;
+    void *tmp = nullptr;
+    if (s->bricked)
+    {
+        void *dst = d_out;
+        if (narrow) { VRT_CUDA(cudaMallocAsync(&tmp, nelem * elem_size(s->store), st)); dst = tmp; }
+        int rc = brick_convert(s, s->d_volume, dst, 0, st);
+        if (rc) { if (tmp) cudaFreeAsync(tmp, st); return rc; }
+        lin = dst;
+    }
+    if (narrow)
+    {
+        narrow_f32_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>((const float *)lin, (short *)d_out, nelem);
+        ++g_launches;
+        cudaError_t e = cudaGetLastError();
+        if (tmp) cudaFreeAsync(tmp, st);
+        VRT_CUDA(e);
+    }
     return VRT_OK;
 }
 
@@ -222,7 +289,7 @@ int vrt_scene_create(vrt_scene **out, int device, int dim, const uint64_t *bound
     }
     cudaFree(tmp);
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
-    rc = apply_layout_flag(s, flags);
+    rc = apply_storage(s, flags);
     if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
@@ -241,7 +308,7 @@ int vrt_scene_create_interleaved(vrt_scene **out, int device, int dim, const uin
     cudaError_t e = cudaMemcpy(s->d_volume, volume_interleaved, s->nvox * (dim + 1) * elem_size(diff_dtype), cudaMemcpyHostToDevice);
     e = e == cudaSuccess ? cudaMemcpy(s->d_translucency, translucency_cropped, s->nvox * 4, cudaMemcpyHostToDevice) : e;
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
-    rc = apply_layout_flag(s, flags);
+    rc = apply_storage(s, flags);
     if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
@@ -272,7 +339,7 @@ int vrt_scene_create_device(vrt_scene **out, int device, int dim, const uint64_t
             e = e == cudaSuccess ? cudaMemset(s->d_translucency, 0xFF, s->nvox * 4) : e;
         if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
     }
-    rc = apply_layout_flag(s, flags);
+    rc = apply_storage(s, flags);
     if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
@@ -365,7 +432,7 @@ int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64
     if (e != cudaSuccess) { vrt_scene_destroy(s); cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); }
     if (flags_h[0]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "refraction-index underflow"); }   // image_util.cpp:536-541,607-610
     if (flags_h[1]) { vrt_scene_destroy(s); return fail(VRT_ERR_INVALID, "differention overflow"); }        // image_util.cpp:293-296
-    rc = apply_layout_flag(s, flags);
+    rc = apply_storage(s, flags);
     if (rc) { vrt_scene_destroy(s); return rc; }
     *out = s;
     return VRT_OK;
@@ -389,17 +456,18 @@ int vrt_scene_download(const vrt_scene *s, void *host_volume, uint32_t *host_tra
 {
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     DeviceGuard g(s->device);
-    if (host_volume && s->bricked)      // hand out the reference's linear layout
+    const size_t bytes = s->nvox * (s->dim + 1) * elem_size(s->dtype);
+    if (host_volume && (s->bricked || s->store != s->dtype))      // hand out the reference's layout and element type
     {
         void *tmp = nullptr;
-        VRT_CUDA(cudaMalloc(&tmp, s->nvox * 4 * elem_size(s->dtype)));
-        int rc = convert_layout(s, s->d_volume, tmp, 0, nullptr);
-        cudaError_t e = rc == VRT_OK ? cudaMemcpy(host_volume, tmp, s->nvox * 4 * elem_size(s->dtype), cudaMemcpyDeviceToHost) : cudaSuccess;
+        VRT_CUDA(cudaMalloc(&tmp, bytes));
+        int rc = linearise(s, tmp, nullptr);
+        cudaError_t e = rc == VRT_OK ? cudaMemcpy(host_volume, tmp, bytes, cudaMemcpyDeviceToHost) : cudaSuccess;
         cudaFree(tmp);
         if (rc) return rc;
         VRT_CUDA(e);
     }
-    else if (host_volume) VRT_CUDA(cudaMemcpy(host_volume, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToHost));
+    else if (host_volume) VRT_CUDA(cudaMemcpy(host_volume, s->d_volume, bytes, cudaMemcpyDeviceToHost));
     if (host_translucency && s->d_translucency) VRT_CUDA(cudaMemcpy(host_translucency, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToHost));
     return VRT_OK;
 }
@@ -409,8 +477,7 @@ int vrt_scene_export_device(const vrt_scene *s, void *d_volume_out, uint32_t *d_
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (d_volume_out && s->bricked) { int rc = convert_layout(s, s->d_volume, d_volume_out, 0, st); if (rc) return rc; }
-    else if (d_volume_out) VRT_CUDA(cudaMemcpyAsync(d_volume_out, s->d_volume, s->nvox * (s->dim + 1) * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
+    if (d_volume_out) { int rc = linearise(s, d_volume_out, st); if (rc) return rc; }
     if (d_translucency_out && s->d_translucency) VRT_CUDA(cudaMemcpyAsync(d_translucency_out, s->d_translucency, s->nvox * 4, cudaMemcpyDeviceToDevice, st));
     return VRT_OK;
 }
@@ -549,7 +616,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     const int block = (int)s->opt_block.load();
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
-    cudaError_t e = s->dtype == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
+    cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
                                         : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
     VRT_CUDA(e);
     return VRT_OK;
@@ -589,7 +656,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
 
     // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
-    if (chunk == 0) chunk = n <= (1u << 20) ? n : std::max<uint64_t>(1u << 20, (n + 7) / 8);
+    if (chunk == 0) chunk = n <= (1u << 19) ? n : std::max<uint64_t>(1u << 19, (n + 15) / 16);
     if (want_path)
     {
         const uint64_t per_ray = (uint64_t)iterations * dim * 4;

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include "cuda_volume_raytracer.h"   // found via -I$(REF_SRC)
 #include "image_util.h"
+#include <fstream>
 
 #include <cstring>
 #include <string>
@@ -99,6 +100,34 @@ void vrtref_scene_iorlog_f32(void *h, float *out)   { auto &s = *static_cast<Sce
 void vrtref_scene_iorlog_u32(void *h, int32_t *out) { auto &s = *static_cast<SceneBox<ior_t, iorlog_t, diff_t>*>(h)->scene; std::memcpy(out, s._ior_log.data(), s._ior_log.size() * sizeof(int32_t)); }
 void vrtref_scene_translucency_cropped_f32(void *h, uint32_t *out) { auto &s = *static_cast<SceneBox<float, float, float>*>(h)->scene; std::memcpy(out, s._translucency_cropped.data(), s._translucency_cropped.size() * 4); }
 void vrtref_scene_translucency_cropped_u32(void *h, uint32_t *out) { auto &s = *static_cast<SceneBox<ior_t, iorlog_t, diff_t>*>(h)->scene; std::memcpy(out, s._translucency_cropped.data(), s._translucency_cropped.size() * 4); }
+
+// the reference's own serializer (serialize.h, image_util.cpp:35-144): what it writes, our reader must read and vice versa
+int vrtref_write_scene_instance_u32(const char *path, const size_t *bounds, int dim, const uint32_t *ior, const uint32_t *tr)
+{
+    VRTREF_TRY
+    RayTraceSceneInstance<ior_t> inst;
+    inst._bound_vec.assign(bounds, bounds + dim);
+    size_t n = 1; for (int d = 0; d < dim; ++d) n *= bounds[d];
+    inst._ior.assign(ior, ior + n); inst._translucency.assign(tr, tr + n);
+    std::ofstream out(path, std::ios::binary);
+    SERIALIZE::write_value(out, inst);
+    VRTREF_CATCH
+}
+// reads a combined instance with the reference's reader and traces it with the reference CPU path
+int vrtref_replay_instance_u32(const char *path, size_t *n_rays, uint32_t *epos, int16_t *edir, uint32_t *eit, size_t cap)
+{
+    VRTREF_TRY
+    RaytraceInstance<ior_t, dir_t> inst;
+    std::ifstream in(path, std::ios::binary);
+    SERIALIZE::read_value(in, inst);
+    std::vector<pos_t> ep; std::vector<dir_t> ed; std::vector<uint32_t> ei; std::vector<brightness_t> rl; std::vector<pos_t> pa;
+    Options opt;
+    trace_rays<ior_t, iorlog_t, diff_t, dir_t>(inst, ep, ed, ei, rl, pa, opt);
+    *n_rays = ei.size();
+    if (ei.size() > cap) throw std::runtime_error("output buffers too small");
+    std::memcpy(epos, ep.data(), ep.size() * 4); std::memcpy(edir, ed.data(), ed.size() * 2); std::memcpy(eit, ei.data(), ei.size() * 4);
+    VRTREF_CATCH
+}
 
 // host interpolator<T> (image_util.h:348-431) -- pins axis order / fraction semantics (image_util_test.h:4-35)
 int vrtref_interpolate_f32(const float *img, const size_t *bounds, int dim, const uint32_t *pos, size_t n, float *out)

@@ -509,3 +509,21 @@ def test_int16_scene_staging_variants_agree(vrt, oracle):
         _assert_same(t.trace_rays_cu(pos, d, [1, 1, 1], 0, 300, trace_paths=True), want, "staging")
         back, _ = t.download_volume()
         assert back.dtype == np.int16 and EQ(back, vol)
+
+
+def test_dropin_splits_large_batches_across_devices(vrt, oracle):
+    """> 32 768 rays through the reference C++ API on the drop-in: on a multi-GPU box the shim keeps a scene per device
+    and traces contiguous chunks concurrently (the reference's multi-device model, cu:676-686,820-843); on one GPU it is a
+    single chunk.  Either way: same bits as the oracle."""
+    from oracle import ref
+    if not ref.available("dropin"):
+        pytest.skip("oracle/_ref/libvrt_dropin.so not built")
+    shape = (40, 36, 34)
+    ior, tr = S.random_scene(shape, seed=43, kind="f32", opaque_fraction=0.005)
+    pos, d = S.random_rays(shape, 100003, seed=9)
+    sc = ref.RefScene(shape, ior, tr, which="dropin")
+    got = sc.trace(pos, d, [1, 1, 1], 0, 200)
+    ob, _, planes, trc = oracle.prep(shape, ior, tr)
+    p2, d2 = oracle.normalise(shape, ior, pos, d)
+    want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 200, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])

@@ -603,6 +603,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.volume = s->d_volume; p.translucency = s->d_translucency;
     p.by = (uint32_t)s->bounds[1]; p.bz = (uint32_t)s->bounds[2];
     p.limx = (uint32_t)((s->bounds[0] - 1) & 0xFFFF); p.limy = (uint32_t)((s->bounds[1] - 1) & 0xFFFF); p.limz = (uint32_t)((s->bounds[2] - 1) & 0xFFFF);
+    p.limx16 = p.limx << 16; p.limy16 = p.limy << 16; p.limz16 = p.limz << 16;
     p.invx = invscale[0]; p.invy = invscale[1]; p.invz = s->dim == 3 ? invscale[2] : 0.0f;
     p.iterations = iterations; p.min_brightness = minb; p.n = n;
     p.pos = d_pos; p.dir = d_dir; p.epos = d_epos; p.edir = d_edir; p.eit = d_eit; p.light = d_light; p.path = d_path;

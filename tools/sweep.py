@@ -131,6 +131,28 @@ def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=True):
     sc.close()
 
 
+def cfg_latency():
+    """small batches through the host call: the reference's own perf instrument is 2000 rays (performance_test.h:9-86)"""
+    from oracle import ref
+    size = 64
+    ior = W.ior_sines(size, period=32.0); tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    sc = vrt.RaytraceScene(ior.shape, ior, tr)
+    co = sc._calculation_object
+    vol, trc = co.download_volume()
+    planes = [np.ascontiguousarray(vol[:, a]) for a in range(3)]
+    rt = ref.RefTracer(co._output_sizes, planes, trc, cuda=True) if ref.available(cuda=True) else None
+    for n in (256, 2048, 16384, 131072):
+        pos, d = W.rays_random(n, 4.0, size - 5.0, 7)
+        pos = pos - np.uint32(0x10000)
+        for name, fn in (("ours", lambda: co.trace_rays_cu(pos, d, [1, 1, 1], 0, 1024)), ("refcuda", (lambda: rt.trace(pos, d, [1, 1, 1], 0, 1024)) if rt else None)):
+            if fn is None:
+                continue
+            fn(); ts = []
+            for _ in range(5):
+                t0 = time.perf_counter(); out = fn(); ts.append(time.perf_counter() - t0)
+            print(json.dumps(dict(cfg="latency", impl=name, rays=n, ms=round(min(ts) * 1e3, 3), steps=int(out[2].astype(np.int64).sum()))), flush=True)
+
+
 def cfg_l2():
     import ctypes as C
     for mb in (16, 32, 48, 64, 256, 4096):
@@ -144,4 +166,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2}[w]()
+        {"c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()

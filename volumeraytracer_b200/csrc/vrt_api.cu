@@ -119,6 +119,15 @@ static int new_scene(vrt_scene **out, int device, int dim, const uint64_t *bound
     for (int d = 0; d < dim; ++d) s->bounds[d] = bounds[d];
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
+    // per-call ray buffers come from the stream-ordered allocator: keep freed blocks cached in the pool between calls
+    // (the reference cudaMalloc/cudaFree's its ray buffers on every call, cu:837-841,958-966)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     *out = s;
     return VRT_OK;
 }
@@ -623,6 +632,39 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     return VRT_OK;
 }
 
+// Per host thread and device: the two pipeline streams of vrt_trace and a pinned/device staging pair for small
+// batches.  Created on first use, reused by every later call of that thread (stream creation and pinned allocation
+// cost more than a small trace), released when the thread exits.
+struct ThreadCtx
+{
+    static constexpr size_t kSmallBytes = 1u << 20;
+    int device = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    char *h_stage = nullptr;   // pinned
+    char *d_stage = nullptr;
+    bool ensure(int dev)
+    {
+        if (device == dev) return true;
+        release();
+        if (cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+        if (cudaMallocHost((void **)&h_stage, kSmallBytes) != cudaSuccess || cudaMalloc((void **)&d_stage, kSmallBytes) != cudaSuccess)
+        { cudaGetLastError(); release(); return false; }
+        device = dev;
+        return true;
+    }
+    void release()
+    {
+        for (int i = 0; i < 2; ++i) if (st[i]) { cudaStreamDestroy(st[i]); st[i] = nullptr; }
+        if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; }
+        if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
+        device = -1;
+        cudaGetLastError();
+    }
+    ~ThreadCtx() { /* the CUDA context may already be gone at thread/process exit: leak on purpose */ }
+};
+static thread_local ThreadCtx t_ctx;
+
 extern "C" {
 
 int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
@@ -654,6 +696,32 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     const size_t ds = elem_size(dir_dtype);
     const bool want_path = flags & VRT_TRACE_PATHS;
     const bool refill = s->opt_refill.load() > 0 && dim == 3;
+    if (!t_ctx.ensure(s->device)) return fail(VRT_ERR_CUDA, "could not create the per-thread streams / staging buffers");
+
+    // Small batches (latency path): one packed H2D, one launch, one packed D2H through pinned staging -- 2 copies instead
+    // of 6, no allocation.  Static ray-to-thread mapping (the grid covers the batch at once, nothing to refill).
+    {
+        const size_t b_pos = (size_t)n * dim * 4, b_dir = ((size_t)n * dim * ds + 3) & ~(size_t)3, b_u32 = (size_t)n * 4;
+        if (!want_path && s->opt_chunk.load() == 0 && b_pos + b_dir + 2 * b_u32 <= ThreadCtx::kSmallBytes)
+        {
+            cudaStream_t q = t_ctx.st[0];
+            char *h = t_ctx.h_stage, *d = t_ctx.d_stage;
+            memcpy(h, pos, b_pos);
+            memcpy(h + b_pos, dir, (size_t)n * dim * ds);
+            VRT_CUDA(cudaMemcpyAsync(d, h, b_pos + b_dir, cudaMemcpyHostToDevice, q));
+            uint32_t *d_pos = (uint32_t *)d; void *d_dir = d + b_pos;
+            uint32_t *d_eit = (uint32_t *)(d + b_pos + b_dir), *d_light = (uint32_t *)(d + b_pos + b_dir + b_u32);
+            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, nullptr, nullptr, q);
+            if (rc) return rc;
+            VRT_CUDA(cudaMemcpyAsync(h, d, b_pos + b_dir + 2 * b_u32, cudaMemcpyDeviceToHost, q));
+            VRT_CUDA(cudaStreamSynchronize(q));
+            memcpy(epos, h, b_pos);
+            memcpy(edir, h + b_pos, (size_t)n * dim * ds);
+            memcpy(eit, h + b_pos + b_dir, b_u32);
+            memcpy(light, h + b_pos + b_dir + b_u32, b_u32);
+            return VRT_OK;
+        }
+    }
 
     // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
@@ -664,9 +732,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         const uint64_t cap = std::max<uint64_t>(1, (1ull << 31) / std::max<uint64_t>(per_ray, 1));     // <= 2 GiB of polyline per chunk
         chunk = std::min(chunk, cap);
     }
-    cudaStream_t st[2] = {nullptr, nullptr};
-    VRT_CUDA(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
-    if (cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(st[0]); return fail(VRT_ERR_CUDA, "cudaStreamCreate failed"); }
+    cudaStream_t st[2] = {t_ctx.st[0], t_ctx.st[1]};
 
     int result = VRT_OK;
     int which = 0;
@@ -708,7 +774,6 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     {
         cudaError_t e = cudaStreamSynchronize(st[i]);
         if (e != cudaSuccess && result == VRT_OK) { result = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
-        cudaStreamDestroy(st[i]);
     }
     return result;
 }

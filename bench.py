@@ -342,6 +342,18 @@ def run_ours(args, rank, local_rank, world):
                 "launch_ms": launch_s * 1e3,
                 "note": "coherent bundle: the 8-corner gathers are served from registers/L1 (cell cache), so the algorithmic gather "
                         "rate exceeds DRAM bandwidth; see roofline_l2 and profiles/ for the counters"}
+        # what actually bounds the kernel on this coherent workload is instruction issue: report that
+        # utilisation too, from the committed ncu instruction count per warp-step and the clock sampled in this run
+        roof_issue = None
+        try:
+            wi = json.load(open(prof)).get("warp_instructions_per_warp_step")
+            sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+            peak_issue = 148 * 4 * sm_hz * 1e6                      # one warp-instruction per scheduler per clock, 4 schedulers per SM
+            ach_issue = wi * (steps_local / 32.0) / launch_s
+            roof_issue = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s", "frac": ach_issue / peak_issue,
+                          "warp_instructions_per_warp_step": wi, "source": "profiles/ncu_c5_summary.json (ncu smsp__inst_executed.sum)"}
+        except Exception:
+            roof_issue = None
         g = C.c_double(0.0)
         roof_l2 = None
         if vrt.lib().vrt_measure_gather_bandwidth(local_rank, 32 << 20, 32, 3, C.byref(g)) == 0 and g.value > 0:
@@ -353,7 +365,7 @@ def run_ours(args, rank, local_rank, world):
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "G ray-steps/s", "h2d_bytes_per_step": n_local * 24 * world, "d2h_bytes_per_step": n_local * 32 * world,
                     "steps": e2e_steps, "matches_device_run": e2e_ok, "call": "vrt_trace (C ABI, pinned host buffers)"},
-            "gpu_launches": int(l_all.item()), "roofline": roof, "roofline_l2": roof_l2,
+            "gpu_launches": int(l_all.item()), "roofline": roof, "roofline_l2": roof_l2, "roofline_issue": roof_issue,
             "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast_s": round(bcast_s, 3),
             "kernel": {"variant": scene.get_option(vrt.VRT_OPT_KERNEL), "block": scene.get_option(vrt.VRT_OPT_BLOCK_THREADS),
                        "refill": scene.get_option(vrt.VRT_OPT_REFILL), "steps_per_poll": scene.get_option(vrt.VRT_OPT_STEPS_PER_POLL)},

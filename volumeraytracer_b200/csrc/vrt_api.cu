@@ -532,8 +532,9 @@ template <typename VoxT, bool DIR_I16, bool LIVE, bool PATH, int KVER>
 static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, cudaStream_t st)
 {
     auto kern = march3_kernel<VoxT, DIR_I16, LIVE, PATH, KVER>;
-    static std::atomic<bool> carved{false};     // the marcher uses no shared memory: give the whole unified array to L1
-    if (!carved.exchange(true)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    static std::atomic<unsigned long long> carved{0};  // per device: the marcher uses no shared memory, give the unified array to L1
+    const unsigned long long bit = 1ull << (s->device & 63);
+    if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     unsigned grid;
     if (p.refill == 0) grid = (unsigned)((p.n + block - 1) / block);
     else
@@ -661,7 +662,7 @@ struct ThreadCtx
         device = -1;
         cudaGetLastError();
     }
-    ~ThreadCtx() { /* the CUDA context may already be gone at thread/process exit: leak on purpose */ }
+    ~ThreadCtx() { release(); }   // at process exit the runtime may already be unloading: the calls then fail harmlessly
 };
 static thread_local ThreadCtx t_ctx;
 

@@ -25,8 +25,17 @@ def _path(which):
     return {False: LIB_PATH, "cpu": LIB_PATH, True: CUDA_LIB_PATH, "cuda": CUDA_LIB_PATH, "dropin": DROPIN_LIB_PATH}[which]
 
 
+def _host_has_avx512():
+    """oracle/_ref is built with -march=x86-64-v4 (the reference needs AVX-512BW/VL, cu:176): do not load it elsewhere."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return all(f in flags for f in ("avx512f", "avx512bw", "avx512vl", "avx2", "fma"))
+    except OSError:
+        return False
+
+
 def available(cuda=False):
-    return os.path.exists(_path(cuda))
+    return os.path.exists(_path(cuda)) and _host_has_avx512()
 
 
 def lib(cuda=False):

@@ -65,7 +65,11 @@ enum {
     /* By default the device copy of an int16 (diff_t) 3-D scene is widened to float when it fits (<= 24 GiB): the marcher
      * converts int16 to float before its first multiply anyway (cu:164), so results are bit-identical while the conversions
      * leave the hot loop (+37 % on coherent bundles, at twice the device memory).  This flag keeps the 8-byte voxels. */
-    VRT_SCENE_KEEP_I16 = 1u << 2
+    VRT_SCENE_KEEP_I16 = 1u << 2,
+    /* layout study: additionally stage the (float) volume in a CUDA 3-D array (block-linear tiling) and fetch the corners
+     * through a point-sampled float4 texture object; filtering stays in software (hardware trilinear has 8-bit weights, the
+     * reference uses 16).  3-D only, no path output; results bit-identical.  Not with VRT_SCENE_BORROW / _KEEP_I16 / _BRICK. */
+    VRT_SCENE_LAYOUT_TEXTURE = 1u << 3
 };
 
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */

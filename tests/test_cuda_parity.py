@@ -527,3 +527,58 @@ def test_dropin_splits_large_batches_across_devices(vrt, oracle):
     p2, d2 = oracle.normalise(shape, ior, pos, d)
     want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 200, round_mode=oracle.ROUND_DEVICE)
     assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])
+
+
+def test_randomised_configurations(vrt, oracle):
+    """Seeded fuzz over shapes (odd / tiny / elongated), element types, invscale, iteration caps, live translucency,
+    paths, launch options and volume layout: the CUDA path must equal the oracle bit for bit every time."""
+    rng = np.random.default_rng(20261018)
+    for case in range(40):
+        dim = 3 if case % 5 else 2
+        shape = tuple(int(x) for x in rng.integers(5, 40, size=dim))
+        volk = "f32" if rng.random() < 0.5 else "i16"
+        dirk = "f32" if rng.random() < 0.5 else "i16"
+        live = bool(rng.random() < 0.4)
+        paths = bool(rng.random() < 0.3)
+        bricked = bool(dim == 3 and not paths and rng.random() < 0.3)
+        iters = int(rng.choice([1, 2, 3, 17, 64, 257, 1000]))
+        n = int(rng.choice([1, 5, 32, 33, 100, 1000, 4097]))
+        isc = [float(x) for x in rng.choice([0.5, 1.0, 1.0, 1.5, 2.0], size=dim)]
+        ior, tr = S.random_scene(shape, seed=1000 + case, kind="f32" if volk == "f32" else "u32", opaque_fraction=float(rng.choice([0.0, 0.01, 0.2])))
+        ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+        if live:
+            trc = trc.copy(); trc[trc != 0] -= np.uint32(1 << int(rng.integers(16, 27)))
+        vol = oracle.fold(planes, trc)
+        pos, d = S.random_rays(ob, n, seed=2000 + case, dir_kind=dirk, scale=float(rng.choice([0.3, 1.0, 1.7])))
+        pos = pos - np.uint32(0x10000) + np.uint32(int(rng.integers(0, 0x10000)))
+        if n > 4:                       # a few rays that start outside / on the boundary / with zero direction
+            pos[0, 0] = np.uint32((ob[0] - 1) << 16); pos[1, 0] = np.uint32(0xFFFF0000); d[2] = 0
+        minb = int(rng.choice([0, 0x40000000, 0xF0000000]))
+        want = oracle.trace(vol, ob, pos, d, isc, iters, translucency=trc if live else None, min_brightness=minb, trace_path=paths,
+                            round_mode=oracle.ROUND_DEVICE)
+        t = vrt.TraceRaysCu(ob, planes, trc, bricked=bricked, keep_i16=bool(rng.random() < 0.5))
+        if dim == 3:
+            t.set_option(vrt.VRT_OPT_KERNEL, int(rng.choice([0, 1, 2, 3])))
+            t.set_option(vrt.VRT_OPT_REFILL, int(rng.choice([0, 1, 7, 32])))
+            t.set_option(vrt.VRT_OPT_STEPS_PER_POLL, int(rng.choice([1, 3, 32, 500])))
+            t.set_option(vrt.VRT_OPT_BLOCK_THREADS, int(rng.choice([32, 64, 128, 256])))
+            t.set_option(vrt.VRT_OPT_CHUNK_RAYS, int(rng.choice([0, 0, 7, 1000])))
+        got = t.trace_rays_cu(pos, d, isc, minb, iters, trace_paths=paths, live_translucency=live)
+        _assert_same(got, want, "case %d shape %s vol %s dir %s live %s paths %s brick %s iters %d n %d" % (case, shape, volk, dirk, live, paths, bricked, iters, n))
+        t.close()
+
+
+@pytest.mark.parametrize("volk", ["f32", "i16"])
+def test_texture_layout_is_bit_identical(vrt, oracle, volk):
+    """VRT_SCENE_LAYOUT_TEXTURE: corners point-sampled from a block-linear CUDA 3-D array -- same bits out."""
+    shape = (31, 36, 29)
+    ior, tr = S.random_scene(shape, seed=19, kind="f32" if volk == "f32" else "u32", opaque_fraction=0.004)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    vol = oracle.fold(planes, trc)
+    pos, d = S.random_rays(ob, 8000, seed=3, dir_kind="f32", scale=1.2)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.25, 0.8], 300, round_mode=oracle.ROUND_DEVICE)
+    t = vrt.TraceRaysCu(ob, planes, trc, texture=True)
+    for refill in (0, 1, 32):
+        t.set_option(vrt.VRT_OPT_REFILL, refill)
+        _assert_same(t.trace_rays_cu(pos, d, [1.0, 1.25, 0.8], 0, 300), want[:4], "texture refill=%d" % refill)

@@ -75,6 +75,8 @@ struct vrt_scene
     uint32_t *d_translucency = nullptr;
     bool      owns = true;
     bool      bricked = false;     // VRT_SCENE_LAYOUT_BRICK
+    cudaArray_t tex_array = nullptr;   // VRT_SCENE_LAYOUT_TEXTURE: block-linear copy + point-sampled texture object
+    cudaTextureObject_t tex = 0;
     uint64_t  nb[3] = {1, 1, 1};   // bricks per axis
     // kept only by vrt_scene_create_from_ior, for vrt_normalise_rays_device (f2)
     void     *d_ior = nullptr;
@@ -193,6 +195,27 @@ static int apply_storage(vrt_scene *s, unsigned flags)
         }
         else cudaGetLastError();       // not enough memory for the wide copy: keep int16
     }
+    if (flags & VRT_SCENE_LAYOUT_TEXTURE)
+    {
+        if (s->dim != 3 || s->store != VRT_F32 || (flags & VRT_SCENE_LAYOUT_BRICK))
+            return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_TEXTURE needs a 3-D scene staged as float and excludes VRT_SCENE_LAYOUT_BRICK / _KEEP_I16 / _BORROW");
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+        VRT_CUDA(cudaMalloc3DArray(&s->tex_array, &desc, make_cudaExtent(s->bounds[2], s->bounds[1], s->bounds[0])));
+        cudaMemcpy3DParms cp;
+        memset(&cp, 0, sizeof cp);
+        cp.srcPtr = make_cudaPitchedPtr(s->d_volume, s->bounds[2] * sizeof(float4), s->bounds[2], s->bounds[1]);
+        cp.dstArray = s->tex_array;
+        cp.extent = make_cudaExtent(s->bounds[2], s->bounds[1], s->bounds[0]);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        VRT_CUDA(cudaMemcpy3D(&cp));
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = s->tex_array;
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        VRT_CUDA(cudaCreateTextureObject(&s->tex, &rd, &td, nullptr));
+        return VRT_OK;
+    }
     if (!(flags & VRT_SCENE_LAYOUT_BRICK)) return VRT_OK;
     if (s->dim != 3) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK is 3-D only");
     if (!s->owns) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK cannot be combined with VRT_SCENE_BORROW");
@@ -259,6 +282,8 @@ int vrt_scene_destroy(vrt_scene *s)
 {
     if (!s) return VRT_OK;
     DeviceGuard g(s->device);
+    if (s->tex) cudaDestroyTextureObject(s->tex);
+    if (s->tex_array) cudaFreeArray(s->tex_array);
     if (s->owns) { cudaFree(s->d_volume); cudaFree(s->d_translucency); }
     if (s->owns_ior) cudaFree(s->d_ior);
     cudaGetLastError();
@@ -562,6 +587,7 @@ static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path
     case 1: return launch3<VoxT, DIR_I16, LIVE, false, 1>(s, p, block, st);
     case 2: return launch3<VoxT, DIR_I16, LIVE, false, 2>(s, p, block, st);
     case 4: return launch3<VoxT, DIR_I16, LIVE, false, 4>(s, p, block, st);
+    case 5: return launch3<VoxT, DIR_I16, LIVE, false, 5>(s, p, block, st);
     default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
     }
 }
@@ -598,7 +624,7 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     if ((flags & VRT_TRACE_PATHS) && n && !path) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs a path buffer");
     if ((flags & VRT_TRACE_PATHS) && iterations == 0) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs iterations >= 1");
     if ((flags & VRT_TRACE_LIVE_TRANSLUCENCY) && !s->d_translucency) return fail(VRT_ERR_INVALID, "scene has no translucency plane");
-    if ((flags & VRT_TRACE_PATHS) && s->bricked) return fail(VRT_ERR_UNSUPPORTED, "path output is not implemented for VRT_SCENE_LAYOUT_BRICK scenes");
+    if ((flags & VRT_TRACE_PATHS) && (s->bricked || s->tex)) return fail(VRT_ERR_UNSUPPORTED, "path output is not implemented for VRT_SCENE_LAYOUT_BRICK / _TEXTURE scenes");
     if (n >= (1ull << 40)) return fail(VRT_ERR_INVALID, "too many rays");
     return VRT_OK;
 }
@@ -623,6 +649,8 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     int kver = (int)s->opt_kernel.load();
     if (kver == 0) kver = 3;
     if (s->bricked) kver = 4;
+    if (s->tex) kver = 5;
+    p.tex = s->tex;
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));

@@ -582,3 +582,39 @@ def test_texture_layout_is_bit_identical(vrt, oracle, volk):
     for refill in (0, 1, 32):
         t.set_option(vrt.VRT_OPT_REFILL, refill)
         _assert_same(t.trace_rays_cu(pos, d, [1.0, 1.25, 0.8], 0, 300), want[:4], "texture refill=%d" % refill)
+
+
+@pytest.mark.parametrize("volk", ["f32", "i16"])
+@pytest.mark.parametrize("live", [False, True])
+def test_empty_space_fast_path_is_bit_identical(vrt, oracle, volk, live):
+    """KVER 6: in cells whose 8 corners have zero gradient the step is re-used instead of recomputed.  A lens in air (flat
+    outside, curved inside), rays with -0.0 and 0.0 direction components, live translucency, and a volume with -0.0 gradients
+    (which must NOT count as flat) all have to come out exactly as the oracle computes them."""
+    from volumeraytracer_b200 import workloads as W
+    size = 48
+    ior = W.ior_luneburg(size, 14.0)
+    if volk == "i16":
+        ior = W.ior_to_u32(ior)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    ob, iorlog, planes, trc = oracle.prep(ior.shape, ior, tr)
+    if live:
+        trc = trc.copy().reshape(ob); trc[:, :, ::3] -= np.uint32(1 << 22); trc[30:34, 20:26, 20:26] = 0; trc = trc.reshape(-1)
+    if volk == "f32":
+        planes[1][::7] = np.where(planes[1][::7] == 0, np.float32(-0.0), planes[1][::7])      # -0 is not +0: not flat
+    vol = oracle.fold(planes, trc)
+    pos, d = S.random_rays(ob, 12000, seed=5, dir_kind="f32" if volk == "f32" else "i16", scale=1.0)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    d[:3000, 1] = 0; d[1000:2000, 2] = 0                       # axis-aligned rays keep exact zeros in the direction
+    if volk == "f32":
+        d[:500, 1] = np.float32(-0.0)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.0, 1.0], 700, translucency=trc if live else None, min_brightness=0x40000000,
+                        round_mode=oracle.ROUND_DEVICE)
+    t = vrt.TraceRaysCu(ob, planes, trc)
+    assert t.get_option(vrt.VRT_OPT_KERNEL) == 0
+    for kver in (0, 6, 3):
+        for refill in (0, 1, 32):
+            t.set_option(vrt.VRT_OPT_KERNEL, kver); t.set_option(vrt.VRT_OPT_REFILL, refill)
+            got = t.trace_rays_cu(pos, d, [1.0, 1.0, 1.0], 0x40000000, 700, live_translucency=live)
+            _assert_same(got, want[:4], "kver %d refill %d" % (kver, refill))
+    flat_voxels = np.mean((vol[:, 0] == 0) & (vol[:, 1] == 0) & (vol[:, 2] == 0))
+    assert flat_voxels > 0.3

@@ -104,7 +104,18 @@ def cfg_c3(size=512, nray=2048, iterations=4096):
     sc.close()
 
 
-def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=True):
+def cfg_c1(size=64, nray=64, iterations=1024, reps=64):
+    """config 1 geometry (constant index: the whole volume is empty space), replicated to 262 144 rays"""
+    ior = torch.full((size,) * 3, 1.0, dtype=torch.float32, device=dev); tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_parallel_x(nray * 8, nray * 8, 1.5, 61.5, x0=1.5)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    run_variants("c1_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    sc.close()
+
+
+def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=False):
     ior = W.ior_luneburg_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
     sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
     pos, d = W.rays_parallel_x(nray, nray, 30.0, 225.0, x0=2.0)
@@ -167,4 +178,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()
+        {"c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()

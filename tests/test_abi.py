@@ -58,3 +58,23 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert not re.search(r'#include\s*[<"].*vrt_oracle', src), f
                 assert "libvrt_oracle" not in src and "libvrt_ref" not in src, f
+
+
+def test_error_behaviour_mirrors_the_reference():
+    """Argument errors surface as exceptions with the reference's wording where it has one (cu:768-771,
+    image_util.cpp:508-515,558,738-741) -- checked without a GPU because validation happens before any CUDA call."""
+    import volumeraytracer_b200 as vrt
+    with pytest.raises(vrt.VrtError, match="Illegal dimension"):
+        vrt.TraceRaysCu([4, 4, 4, 4], [np.zeros(256, np.float32)] * 4, np.zeros(256, np.uint32))
+    with pytest.raises(ValueError):
+        vrt.TraceRaysCu([4, 4, 4], [np.zeros(64, np.float32)] * 2, np.zeros(64, np.uint32))
+    with pytest.raises(ValueError, match="imagesizes"):
+        vrt.TraceRaysCu([4, 4, 4], [np.zeros(63, np.float32)] * 3, np.zeros(64, np.uint32))
+    with pytest.raises(vrt.VrtError, match="65535"):
+        vrt.TraceRaysCu([70000, 2, 2], [np.zeros(280000, np.float32)] * 3, np.zeros(280000, np.uint32))
+    with pytest.raises(vrt.VrtError, match="dimension is zero"):
+        vrt.RaytraceScene([], np.zeros(0, np.float32), np.zeros(0, np.uint32))
+    with pytest.raises(vrt.VrtError, match="Illegal dimension"):
+        vrt.RaytraceScene([5, 5, 5, 5], np.ones(625, np.float32), np.zeros(625, np.uint32))
+    with pytest.raises(TypeError):
+        vrt.TraceRaysCu([4, 4, 4], [np.zeros(64, np.float64)] * 3, np.zeros(64, np.uint32))

@@ -618,3 +618,41 @@ def test_empty_space_fast_path_is_bit_identical(vrt, oracle, volk, live):
             _assert_same(got, want[:4], "kver %d refill %d" % (kver, refill))
     flat_voxels = np.mean((vol[:, 0] == 0) & (vol[:, 1] == 0) & (vol[:, 2] == 0))
     assert flat_voxels > 0.3
+
+
+def test_reference_python_binding_on_the_dropin(vrt, oracle, tmp_path, monkeypatch):
+    """The reference's OWN pybind11 module (src/python_binding.cpp, unmodified, built by `make dropin_py`) linked against
+    our TraceRaysCu<> drop-in: `cuda_raytrace.cuda_raytrace(...)` -- the reference's Python entry point -- runs on the B200
+    marcher and returns what the oracle predicts.  (Tuple slots 2/3 carry end_iteration / remaining_light: the binding's own
+    slot mix-up, python_binding.cpp:38-45.)"""
+    import glob
+    import importlib.util
+    import os
+    from oracle import ref
+    so = glob.glob(os.path.join(os.path.dirname(ref.LIB_PATH), "cuda_raytrace*.so"))
+    if not so or not ref.available("dropin"):
+        pytest.skip("oracle/_ref/cuda_raytrace*.so not built")
+    spec = importlib.util.spec_from_file_location("cuda_raytrace", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.chdir(tmp_path)                       # the binding writes debug_raytrace_instance into the CWD on every call
+    inp = S.scaling_test_inputs("u32")
+    res = mod.cuda_raytrace(inp["bounds"], inp["ior"].tolist(), inp["translucency"].tolist(), inp["pos"].ravel().tolist(),
+                            inp["dir"].ravel().tolist(), inp["invscale"], 0, inp["iterations"], False)
+    ob, iorlog, planes, trc = oracle.prep(inp["bounds"], inp["ior"], inp["translucency"])
+    p2, d2 = oracle.normalise(inp["bounds"], inp["ior"], inp["pos"], inp["dir"])
+    want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, inp["invscale"], inp["iterations"], round_mode=oracle.ROUND_DEVICE)
+    assert np.array_equal(np.array(res[0], np.uint32).reshape(-1, 3), want[0] + np.uint32(0x10000))
+    assert np.array_equal(np.array(res[1], np.int16).reshape(-1, 3), want[1])
+    assert list(res[2]) == want[2].tolist() == [46734, 46623]
+    assert list(res[3]) == [0xFFFFFFFF, 0xFFFFFFFF]
+    # a larger call: 3000 random rays
+    shape = (24, 20, 28)
+    ior, tr = S.random_scene(shape, seed=13, kind="u32", opaque_fraction=0.01)
+    pos, d = S.random_rays(shape, 3000, seed=5, dir_kind="i16")
+    res = mod.cuda_raytrace(list(shape), ior.ravel().tolist(), tr.ravel().tolist(), pos.ravel().tolist(), d.ravel().tolist(), [1.0, 0.75, 1.5], 0, 400, False)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    p2, d2 = oracle.normalise(shape, ior, pos, d)
+    want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1.0, 0.75, 1.5], 400, round_mode=oracle.ROUND_DEVICE)
+    assert np.array_equal(np.array(res[0], np.uint32).reshape(-1, 3), want[0] + np.uint32(0x10000))
+    assert np.array_equal(np.array(res[1], np.int16).reshape(-1, 3), want[1]) and list(res[2]) == want[2].tolist()

@@ -80,6 +80,8 @@ enum {
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
     VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
+    VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
+                                      extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
     VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an
                                    incoherent batch's working set inside L1/L2 */
 };

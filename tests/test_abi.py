@@ -37,6 +37,9 @@ def test_argument_validation_needs_no_gpu():
     assert lib.vrt_trace(None, 0, None, None, 0, None, 0, 0, 0, None, None, None, None, None) == _lib.VRT_ERR_INVALID
     assert b"scene is null" in lib.vrt_last_error()
     assert lib.vrt_scene_destroy(None) == 0
+    assert lib.vrt_scene_set_option(None, 0, 0) == _lib.VRT_ERR_INVALID
+    g = C.c_double()
+    assert lib.vrt_measure_gather_bandwidth(0, 16, 32, 1, C.byref(g)) == _lib.VRT_ERR_INVALID
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -616,8 +616,9 @@ def test_empty_space_fast_path_is_bit_identical(vrt, oracle, volk, live):
             t.set_option(vrt.VRT_OPT_KERNEL, kver); t.set_option(vrt.VRT_OPT_REFILL, refill)
             got = t.trace_rays_cu(pos, d, [1.0, 1.0, 1.0], 0x40000000, 700, live_translucency=live)
             _assert_same(got, want[:4], "kver %d refill %d" % (kver, refill))
-    flat_voxels = np.mean((vol[:, 0] == 0) & (vol[:, 1] == 0) & (vol[:, 2] == 0))
+    flat_voxels = np.mean((vol[:, 0] == 0) & (vol[:, 1] == 0) & (vol[:, 2] == 0) & (vol[:, 3] <= 0))
     assert flat_voxels > 0.3
+    assert abs(t.get_option(vrt.VRT_INFO_EMPTY_PERMILLE) - 1000 * flat_voxels) <= 1
 
 
 def test_reference_python_binding_on_the_dropin(vrt, oracle, tmp_path, monkeypatch):

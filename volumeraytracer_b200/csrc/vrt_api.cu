@@ -572,6 +572,7 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_CHUNK_RAYS: *v = s->opt_chunk; break;
     case VRT_OPT_STEPS_PER_POLL: *v = s->opt_poll; break;
     case VRT_OPT_MAX_CTAS_PER_SM: *v = s->opt_max_ctas; break;
+    case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -652,7 +653,8 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     if (!invscale) return fail(VRT_ERR_INVALID, "invscale is null");
     if (n && (!pos || !dir || !epos || !edir || !eit || !light)) return fail(VRT_ERR_INVALID, "null ray buffer");
     if ((flags & VRT_TRACE_PATHS) && n && !path) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs a path buffer");
-    if ((flags & VRT_TRACE_PATHS) && iterations == 0) return fail(VRT_ERR_INVALID, "VRT_TRACE_PATHS needs iterations >= 1");
+    // iterations == 0 makes the reference's counter wrap (cu:333: path[--iterations]) and march for 2^32-1 steps
+    if (iterations == 0) return fail(VRT_ERR_INVALID, "iterations must be >= 1");
     if ((flags & VRT_TRACE_LIVE_TRANSLUCENCY) && !s->d_translucency) return fail(VRT_ERR_INVALID, "scene has no translucency plane");
     if ((flags & VRT_TRACE_PATHS) && (s->bricked || s->tex)) return fail(VRT_ERR_UNSUPPORTED, "path output is not implemented for VRT_SCENE_LAYOUT_BRICK / _TEXTURE scenes");
     if (n >= (1ull << 40)) return fail(VRT_ERR_INVALID, "too many rays");

@@ -80,6 +80,10 @@ enum {
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
     VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
+    VRT_OPT_REGION_LOG2   = 6,  /* 0 (default): single-launch marcher.  5..9: opt-in mode for INCOHERENT batches -- the volume is cut into
+                                   regions of 2^k voxels, rays are sorted by region and marched region by region so that the gathers are
+                                   served by L2 instead of DRAM (bit-identical results; 3-D, linear layout, no path output) */
+    VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 16) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
     VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an

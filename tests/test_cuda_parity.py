@@ -657,3 +657,26 @@ def test_reference_python_binding_on_the_dropin(vrt, oracle, tmp_path, monkeypat
     want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1.0, 0.75, 1.5], 400, round_mode=oracle.ROUND_DEVICE)
     assert np.array_equal(np.array(res[0], np.uint32).reshape(-1, 3), want[0] + np.uint32(0x10000))
     assert np.array_equal(np.array(res[1], np.int16).reshape(-1, 3), want[1]) and list(res[2]) == want[2].tolist()
+
+
+@pytest.mark.parametrize("volk,dirk,live", [("f32", "f32", False), ("i16", "i16", True), ("f32", "i16", True), ("i16", "f32", False)])
+def test_region_mode_is_bit_identical(vrt, oracle, volk, dirk, live):
+    """VRT_OPT_REGION_LOG2: rays sorted by region and marched region by region, suspended and resumed across rounds --
+    every step is still the reference's step, so the outputs equal the oracle's whatever the region size / round count."""
+    shape = (70, 45, 81)
+    ior, tr = S.random_scene(shape, seed=23, kind="f32" if volk == "f32" else "u32", opaque_fraction=0.002)
+    ob, iorlog, planes, trc = oracle.prep(shape, ior, tr)
+    if live:
+        trc = trc.copy(); trc[trc != 0] -= np.uint32(1 << 22)
+    vol = oracle.fold(planes, trc)
+    pos, d = S.random_rays(ob, 30000, seed=4, dir_kind=dirk, scale=1.0)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    pos[0] = [0xFFFF0000, 0x20000, 0x20000]; pos[1, 2] = np.uint32((ob[2] - 1) << 16)            # start outside / on the far face
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.0, 1.0], 900, translucency=trc if live else None, min_brightness=0x20000000,
+                        round_mode=oracle.ROUND_DEVICE)
+    t = vrt.TraceRaysCu(ob, planes, trc, keep_i16=(dirk == "f32"))
+    for log2, rounds, refill in ((5, 24, 1), (5, 2, 32), (6, 1, 8), (7, 24, 32)):
+        t.set_option(vrt.VRT_OPT_REGION_LOG2, log2); t.set_option(vrt.VRT_OPT_REGION_ROUNDS, rounds); t.set_option(vrt.VRT_OPT_REFILL, refill)
+        got = t.trace_rays_cu(pos, d, [1.0, 1.0, 1.0], 0x20000000, 900, live_translucency=live)
+        _assert_same(got, want[:4], "region log2=%d rounds=%d refill=%d" % (log2, rounds, refill))
+    assert len(np.unique(want[2])) > 50

@@ -32,12 +32,15 @@ def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
     for var in variants:
         kver, block, refill, poll = var[:4]
         ctas = var[4] if len(var) > 4 else 0
+        region = var[5] if len(var) > 5 else 0
+        co.set_option(vrt.VRT_OPT_REGION_LOG2, region)
+        co.set_option(vrt.VRT_OPT_REGION_ROUNDS, var[6] if len(var) > 6 else 24)
         co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)
         co.set_option(vrt.VRT_OPT_REFILL, refill); co.set_option(vrt.VRT_OPT_STEPS_PER_POLL, poll)
         co.set_option(vrt.VRT_OPT_MAX_CTAS_PER_SM, ctas)
         t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
         steps = int(out[2].to(torch.int64).sum().item())
-        print(json.dumps(dict(cfg=name + ("_brick" if BRICK else "") + ("_tex" if TEX else ""), kver=kver, block=block, refill=refill, poll=poll, ctas=ctas, sec=round(t, 4), steps=steps,
+        print(json.dumps(dict(cfg=name + ("_brick" if BRICK else "") + ("_tex" if TEX else ""), kver=kver, block=block, refill=refill, poll=poll, ctas=ctas, region=region, sec=round(t, 4), steps=steps,
                               grays=round(steps / t / 1e9, 2))), flush=True)
         res.append((steps / t / 1e9, kver, block, refill, poll))
     return res

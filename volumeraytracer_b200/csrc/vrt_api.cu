@@ -13,6 +13,9 @@
 #include "../../include/vrt_b200.h"
 #include "vrt_march.cuh"
 #include "vrt_prep.cuh"
+#include "vrt_region.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -86,7 +89,7 @@ struct vrt_scene
     bool      owns_ior = false;
     int       num_sms = 148;
     // options
-    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{32}, opt_max_ctas{0};
+    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{32}, opt_max_ctas{0}, opt_region{0}, opt_rounds{16};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -556,6 +559,8 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_CHUNK_RAYS:     if (v < 0) return fail(VRT_ERR_INVALID, "chunk must be >= 0"); s->opt_chunk = v; break;
     case VRT_OPT_STEPS_PER_POLL: if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "steps per poll must be 1..4096"); s->opt_poll = v; break;
     case VRT_OPT_MAX_CTAS_PER_SM: if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "max CTAs per SM must be 0..32"); s->opt_max_ctas = v; break;
+    case VRT_OPT_REGION_LOG2:    if (v != 0 && (v < 5 || v > 9)) return fail(VRT_ERR_INVALID, "region log2 must be 0 or 5..9"); s->opt_region = v; break;
+    case VRT_OPT_REGION_ROUNDS:  if (v < 1 || v > 256) return fail(VRT_ERR_INVALID, "region rounds must be 1..256"); s->opt_rounds = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -572,6 +577,8 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_CHUNK_RAYS: *v = s->opt_chunk; break;
     case VRT_OPT_STEPS_PER_POLL: *v = s->opt_poll; break;
     case VRT_OPT_MAX_CTAS_PER_SM: *v = s->opt_max_ctas; break;
+    case VRT_OPT_REGION_LOG2: *v = s->opt_region; break;
+    case VRT_OPT_REGION_ROUNDS: *v = s->opt_rounds; break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
@@ -645,6 +652,80 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
     return live ? launch2_k<VoxT, false, true>(p, path, block, st) : launch2_k<VoxT, false, false>(p, path, block, st);
 }
 
+// ---- region mode (vrt_region.cuh): sort by region, march region by region, all on the caller's stream ---------------
+template <typename VoxT, bool DIR_I16, bool LIVE>
+static cudaError_t launch_region(const vrt_scene *s, const RegionParams &rp, cudaStream_t st)
+{
+    auto kern = march3_region_kernel<VoxT, DIR_I16, LIVE>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+    if (e != cudaSuccess) return e;
+    const int cap = (int)s->opt_max_ctas.load();
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    if (per_sm < 1) per_sm = 1;
+    const unsigned long long want = (rp.m.n + 127) / 128;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)per_sm * s->num_sms, want);
+    kern<<<grid, 128, 0, st>>>(rp);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool di16, bool live, cudaStream_t st)
+{
+    const int k = (int)s->opt_region.load();
+    const uint64_t n = mp.n;
+    const uint32_t e = 1u << k;
+    const uint32_t rx = (uint32_t)((s->bounds[0] + e - 1) / e), ry = (uint32_t)((s->bounds[1] + e - 1) / e), rz = (uint32_t)((s->bounds[2] + e - 1) / e);
+    if ((uint64_t)rx * ry * rz >= kRegionDone) return fail(VRT_ERR_INVALID, "too many regions: raise VRT_OPT_REGION_LOG2");
+    if (n >= (1ull << 32)) return fail(VRT_ERR_INVALID, "region mode takes at most 2^32-1 rays per call");
+
+    // workspace: suspended ray state, two key/order buffers for the sort, cub scratch, the refill counter
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (int)std::min<uint64_t>(n, 0x7FFFFFFF), 0, 16, st);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4);
+    const size_t o_k0 = o_light + al(n * 4), o_k1 = o_k0 + al(n * 2), o_o0 = o_k1 + al(n * 2), o_o1 = o_o0 + al(n * 4);
+    const size_t o_cnt = o_o1 + al(n * 4), o_cub = o_cnt + 256, total = o_cub + al(cub_bytes);
+    char *ws = nullptr;
+    VRT_CUDA(cudaMallocAsync((void **)&ws, total, st));
+    RegionParams rp;
+    rp.m = mp;
+    rp.m.counter = (unsigned long long *)(ws + o_cnt);
+    rp.m.refill = std::max(1, (int)s->opt_refill.load());
+    rp.st_pos = (uint32_t *)(ws + o_pos); rp.st_dir = (float *)(ws + o_dir); rp.st_it = (uint32_t *)(ws + o_it); rp.st_light = (uint32_t *)(ws + o_light);
+    rp.log2_edge = k; rp.margin = std::min<uint32_t>(8u, e / 4); rp.ry = ry; rp.rz = rz;
+    uint16_t *keys[2] = {(uint16_t *)(ws + o_k0), (uint16_t *)(ws + o_k1)};
+    uint32_t *order[2] = {(uint32_t *)(ws + o_o0), (uint32_t *)(ws + o_o1)};
+    int cur = 0;
+    rp.keys = keys[cur]; rp.order = order[cur];
+    const unsigned ib = (unsigned)((n + 255) / 256);
+    if (di16) region_init_kernel<true><<<ib, 256, 0, st>>>(rp, order[cur]);
+    else      region_init_kernel<false><<<ib, 256, 0, st>>>(rp, order[cur]);
+    ++g_launches;
+    cudaError_t err = cudaGetLastError();
+    const int rounds = (int)s->opt_rounds.load();
+    for (int r = 0; r <= rounds && err == cudaSuccess; ++r)
+    {
+        err = cub::DeviceRadixSort::SortPairs(ws + o_cub, cub_bytes, keys[cur], keys[cur ^ 1], order[cur], order[cur ^ 1], (int)n, 0, 16, st);
+        cur ^= 1;
+        g_launches += 1;
+        rp.keys = keys[cur]; rp.order = order[cur];
+        rp.log2_edge = r < rounds ? k : -1;                       // the last round has no region limit: whatever is left runs to its end
+        if (err == cudaSuccess) err = cudaMemsetAsync(rp.m.counter, 0, sizeof(unsigned long long), st);
+        if (err != cudaSuccess) break;
+        if (s->store == VRT_F32)
+            err = di16 ? (live ? launch_region<float, true, true>(s, rp, st) : launch_region<float, true, false>(s, rp, st))
+                       : (live ? launch_region<float, false, true>(s, rp, st) : launch_region<float, false, false>(s, rp, st));
+        else
+            err = di16 ? (live ? launch_region<int16_t, true, true>(s, rp, st) : launch_region<int16_t, true, false>(s, rp, st))
+                       : (live ? launch_region<int16_t, false, true>(s, rp, st) : launch_region<int16_t, false, false>(s, rp, st));
+    }
+    cudaFreeAsync(ws, st);
+    VRT_CUDA(err);
+    return VRT_OK;
+}
+
 static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const void *dir, int dir_dtype, const float *invscale,
                           uint32_t iterations, unsigned flags, const void *epos, const void *edir, const void *eit, const void *light, const void *path)
 {
@@ -686,8 +767,10 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.tex = s->tex;
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
-    if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
+    if (s->opt_region.load() > 0 && s->dim == 3 && !path && !s->bricked && !s->tex)
+        return enqueue_march_regions(s, p, di16, live, st);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
+    if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
                                         : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
     VRT_CUDA(e);

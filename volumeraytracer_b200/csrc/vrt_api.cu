@@ -677,12 +677,12 @@ static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool
     const uint32_t e = 1u << k;
     const uint32_t rx = (uint32_t)((s->bounds[0] + e - 1) / e), ry = (uint32_t)((s->bounds[1] + e - 1) / e), rz = (uint32_t)((s->bounds[2] + e - 1) / e);
     if ((uint64_t)rx * ry * rz >= kRegionDone) return fail(VRT_ERR_INVALID, "too many regions: raise VRT_OPT_REGION_LOG2");
-    if (n >= (1ull << 32)) return fail(VRT_ERR_INVALID, "region mode takes at most 2^32-1 rays per call");
+    if (n >= (1ull << 31)) return fail(VRT_ERR_INVALID, "region mode takes at most 2^31-1 rays per call (cub item count is int)");
 
     // workspace: suspended ray state, two key/order buffers for the sort, cub scratch, the refill counter
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (int)std::min<uint64_t>(n, 0x7FFFFFFF), 0, 16, st);
+                                    (int)n, 0, 16, st);
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4);
     const size_t o_k0 = o_light + al(n * 4), o_k1 = o_k0 + al(n * 2), o_o0 = o_k1 + al(n * 2), o_o1 = o_o0 + al(n * 4);

@@ -478,16 +478,18 @@ int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64
         pp.dim = dim; pp.nin = nin; pp.nout = s->nvox;
         for (int d = 0; d < 3; ++d) { pp.ib[d] = d < dim ? (uint32_t)bounds[d] : 1; pp.ob[d] = d < dim ? (uint32_t)cb[d] : 1; }
         for (int a = 0; a < dim; ++a) make_stamp(dim, a, bounds, &pp.stamp[a]);
-        const unsigned bin = (unsigned)((nin + 255) / 256), bout = (unsigned)((s->nvox + 255) / 256);
+        const unsigned bin = (unsigned)((nin + 255) / 256);
+        const dim3 bout = dim == 3 ? dim3((unsigned)((cb[2] + 127) / 128), (unsigned)cb[1], (unsigned)cb[0])
+                                   : dim3((unsigned)((cb[1] + 127) / 128), (unsigned)cb[0], 1u);
         if (ior_dtype == VRT_F32)
         {
             iorlog_f32_kernel<<<bin, 256>>>((const float *)s->d_ior, (float *)d_iorlog, nin, d_flag);
-            prep_f32_kernel<<<bout, 256>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
+            prep_f32_kernel<<<bout, 128>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
         }
         else
         {
             iorlog_u32_kernel<<<bin, 256>>>((const uint32_t *)s->d_ior, (int32_t *)d_iorlog, nin, d_flag);
-            prep_u32_kernel<<<bout, 256>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
+            prep_u32_kernel<<<bout, 128>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
         }
         g_launches += 2;
         e = cudaGetLastError();

@@ -55,33 +55,27 @@ __global__ void iorlog_u32_kernel(const uint32_t *ior, int32_t *iorlog, unsigned
     iorlog[i] = (int32_t)round(tmp);
 }
 
-__device__ __forceinline__ unsigned long long in_base(const PrepParams &p, unsigned long long o, uint32_t c[3])
+// Output voxel of this thread from the launch geometry -- grid (ceil(oz/128), oy, ox), 128 threads along the contiguous
+// axis -- so no 64-bit division is needed per voxel.  A 2-D volume is treated as one slab (ox = 1, no stencil extent in x).
+// Returns false for the padding threads; o = linear output index, base = element offset of the stencil block's origin.
+__device__ __forceinline__ bool prep_index(const PrepParams &p, unsigned long long &o, unsigned long long &base, unsigned long long &centre)
 {
-    // output voxel o -> coordinates c (axis 0 slowest) and the element offset of the stencil block's origin
-    unsigned long long r = o, base = 0, mul = 1;
-    for (int d = p.dim - 1; d >= 0; --d)
-    {
-        c[d] = (uint32_t)(r % p.ob[d]); r /= p.ob[d];
-        base += (unsigned long long)c[d] * mul; mul *= p.ib[d];
-    }
-    return base;
-}
-
-__device__ __forceinline__ unsigned long long centre_offset(const PrepParams &p)
-{
-    unsigned long long off = 0, mul = 1;
-    for (int d = p.dim - 1; d >= 0; --d) { off += mul; mul *= p.ib[d]; }
-    return off;
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = blockIdx.z;
+    const uint32_t oy = p.dim == 3 ? p.ob[1] : p.ob[0], oz = p.dim == 3 ? p.ob[2] : p.ob[1];
+    const uint32_t iy = p.dim == 3 ? p.ib[1] : p.ib[0], iz = p.dim == 3 ? p.ib[2] : p.ib[1];
+    if (z >= oz) return false;
+    o = ((unsigned long long)x * oy + y) * oz + z;
+    base = ((unsigned long long)x * iy + y) * iz + z;
+    centre = (p.dim == 3 ? (unsigned long long)iy * iz : 0ull) + iz + 1ull;        // crop_matrix :300-319, lower bound 1 per axis
+    return true;
 }
 
 // one thread per cropped voxel: dim gradient channels + extra channel, interleaved; also the cropped translucency plane
 __global__ void prep_f32_kernel(const PrepParams p, const float *iorlog, const uint32_t *translucency,
                                 float *volume, uint32_t *tr_cropped)
 {
-    unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= p.nout) return;
-    uint32_t c[3];
-    const unsigned long long base = in_base(p, o, c);
+    unsigned long long o, base, centre;
+    if (!prep_index(p, o, base, centre)) return;
     const float weight = 812.0f * 256.0f;                                  // image_util.cpp:438
     float out[4];
     for (int ax = 0; ax < p.dim; ++ax)
@@ -91,11 +85,12 @@ __global__ void prep_f32_kernel(const PrepParams p, const float *iorlog, const u
             sum = __fadd_rn(sum, __fmul_rn((float)p.stamp[ax].val[j], iorlog[base + p.stamp[ax].off[j]]));
         out[ax] = __fdiv_rn(sum, weight);                                  // :288-291
     }
-    const uint32_t tr = translucency[base + centre_offset(p)];             // crop_matrix :300-319, lower bound 1
+    const uint32_t tr = translucency[base + centre];
     tr_cropped[o] = tr;
     out[p.dim] = (float)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);   // cu:654-659
     float *dst = volume + o * (unsigned long long)(p.dim + 1);
-    for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+    if (p.dim == 3) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);      // one 16-byte store per voxel
+    else for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
 }
 
 __device__ __forceinline__ int32_t div_round_closest(int32_t n, int32_t d) // image_util.h:34-38
@@ -106,10 +101,8 @@ __device__ __forceinline__ int32_t div_round_closest(int32_t n, int32_t d) // im
 __global__ void prep_u32_kernel(const PrepParams p, const int32_t *iorlog, const uint32_t *translucency,
                                 int16_t *volume, uint32_t *tr_cropped, int *overflow)
 {
-    unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= p.nout) return;
-    uint32_t c[3];
-    const unsigned long long base = in_base(p, o, c);
+    unsigned long long o, base, centre;
+    if (!prep_index(p, o, base, centre)) return;
     const int32_t weight = 812 * 256;
     int16_t out[4];
     for (int ax = 0; ax < p.dim; ++ax)
@@ -121,11 +114,12 @@ __global__ void prep_u32_kernel(const PrepParams p, const int32_t *iorlog, const
         out[ax] = (int16_t)v;
         if ((int32_t)out[ax] != v) *overflow = 1;                          // "differention overflow" :293-296
     }
-    const uint32_t tr = translucency[base + centre_offset(p)];
+    const uint32_t tr = translucency[base + centre];
     tr_cropped[o] = tr;
     out[p.dim] = (int16_t)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);
     int16_t *dst = volume + o * (unsigned long long)(p.dim + 1);
-    for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+    if (p.dim == 3) *reinterpret_cast<short4 *>(dst) = make_short4(out[0], out[1], out[2], out[3]);
+    else for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
 }
 
 // TraceRaysCu ctor on planar inputs (cu:654-669): extra channel + interleave

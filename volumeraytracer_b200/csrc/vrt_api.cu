@@ -411,30 +411,6 @@ int vrt_scene_create_device(vrt_scene **out, int device, int dim, const uint64_t
     return VRT_OK;
 }
 
-// stamp for derivative along `ax` (image_util.cpp:380-425): the base stamp differentiates along the LAST axis; the
-// stamp for axis ax is the base stamp with axes ax and dim-1 swapped; taps are visited in row-major order of the stamp.
-static void make_stamp(int dim, int ax, const uint64_t *ib, Stamp *st)
-{
-    static const int S3[27] = {-14, 0, 14, -47, 0, 47, -14, 0, 14, -47, 0, 47, -162, 0, 162, -47, 0, 47, -14, 0, 14, -47, 0, 47, -14, 0, 14};
-    static const int S2[9] = {-47, 0, 47, -162, 0, 162, -47, 0, 47};
-    const int *base = dim == 3 ? S3 : S2;
-    const int cnt = dim == 3 ? 27 : 9;
-    st->n = 0;
-    for (int j = 0; j < cnt; ++j)
-    {
-        int p[3] = {0, 0, 0}, r = j;
-        for (int d = dim - 1; d >= 0; --d) { p[d] = r % 3; r /= 3; }
-        int q[3] = {p[0], p[1], p[2]};
-        std::swap(q[ax], q[dim - 1]);
-        int lin = 0;
-        for (int d = 0; d < dim; ++d) lin = lin * 3 + q[d];
-        if (base[lin] == 0) continue;
-        long long off = 0;
-        for (int d = 0; d < dim; ++d) off = off * (long long)ib[d] + p[d];
-        st->off[st->n] = (int)off; st->val[st->n] = base[lin]; ++st->n;
-    }
-}
-
 int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64_t *bounds, int ior_dtype,
                               const void *ior, const uint32_t *translucency, int ptrs_on_device, unsigned flags)
 {
@@ -477,19 +453,20 @@ int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, const uint64
         PrepParams pp;
         pp.dim = dim; pp.nin = nin; pp.nout = s->nvox;
         for (int d = 0; d < 3; ++d) { pp.ib[d] = d < dim ? (uint32_t)bounds[d] : 1; pp.ob[d] = d < dim ? (uint32_t)cb[d] : 1; }
-        for (int a = 0; a < dim; ++a) make_stamp(dim, a, bounds, &pp.stamp[a]);
         const unsigned bin = (unsigned)((nin + 255) / 256);
         const dim3 bout = dim == 3 ? dim3((unsigned)((cb[2] + 127) / 128), (unsigned)cb[1], (unsigned)cb[0])
                                    : dim3((unsigned)((cb[1] + 127) / 128), (unsigned)cb[0], 1u);
         if (ior_dtype == VRT_F32)
         {
             iorlog_f32_kernel<<<bin, 256>>>((const float *)s->d_ior, (float *)d_iorlog, nin, d_flag);
-            prep_f32_kernel<<<bout, 128>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
+            if (dim == 3) prep_f32_kernel<3><<<bout, 128>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
+            else          prep_f32_kernel<2><<<bout, 128>>>(pp, (const float *)d_iorlog, d_tr, (float *)s->d_volume, s->d_translucency);
         }
         else
         {
             iorlog_u32_kernel<<<bin, 256>>>((const uint32_t *)s->d_ior, (int32_t *)d_iorlog, nin, d_flag);
-            prep_u32_kernel<<<bout, 128>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
+            if (dim == 3) prep_u32_kernel<3><<<bout, 128>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
+            else          prep_u32_kernel<2><<<bout, 128>>>(pp, (const int32_t *)d_iorlog, d_tr, (int16_t *)s->d_volume, s->d_translucency, d_flag + 1);
         }
         g_launches += 2;
         e = cudaGetLastError();

@@ -14,16 +14,10 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace vrt {
-
-struct Stamp
-{
-    int n;            // number of non-zero taps (18 in 3-D, 6 in 2-D)
-    int off[18];      // element offset inside the uncropped volume, relative to the 3^dim block's origin
-    int val[18];      // tap weight
-};
 
 struct PrepParams
 {
@@ -31,7 +25,6 @@ struct PrepParams
     uint32_t ib[3];   // uncropped bounds (padded at the FRONT with 1 for dim == 2 is NOT done: ib[0..dim-1])
     uint32_t ob[3];   // cropped bounds = ib - 2
     unsigned long long nin, nout;
-    Stamp    stamp[3];
 };
 
 // log(n) * 0x420000 -- float scene: image_util.cpp:611 (double log, double product, narrowed on store)
@@ -70,27 +63,76 @@ __device__ __forceinline__ bool prep_index(const PrepParams &p, unsigned long lo
     return true;
 }
 
-// one thread per cropped voxel: dim gradient channels + extra channel, interleaved; also the cropped translucency plane
+// The stamps (image_util.cpp:421-425) as compile-time tables.  The base stamp differentiates along the LAST axis:
+// S[p0][p1][p2] = W[p0][p1] * D[p2]; the stamp for axis `ax` is the base stamp with axes ax and dim-1 swapped
+// (stamp_t_struct ctor :380-414), and convolution::operator() (:271-291) visits its non-zero taps in row-major order.
+__device__ __forceinline__ constexpr int stamp3_weight(int ax, int p0, int p1, int p2)
+{
+    constexpr int W[3][3] = {{14, 47, 14}, {47, 162, 47}, {14, 47, 14}};
+    constexpr int D[3] = {-1, 0, 1};
+    return ax == 2 ? W[p0][p1] * D[p2] : ax == 0 ? W[p2][p1] * D[p0] : W[p0][p2] * D[p1];
+}
+__device__ __forceinline__ constexpr int stamp2_weight(int ax, int p0, int p1)
+{
+    constexpr int W[3] = {47, 162, 47};
+    constexpr int D[3] = {-1, 0, 1};
+    return ax == 1 ? W[p0] * D[p1] : W[p1] * D[p0];
+}
+
+// Scene prep, one thread per cropped voxel: the 3^dim neighbourhood is read once into registers, the dim stencil sums run
+// fully unrolled in the reference's tap order, then the extra channel, the interleave and the cropped translucency plane.
+// T = float (float scene) or int32_t (int16 scene); arithmetic per type as in convolution::operator().
+template <typename T, int DIM>
+__device__ __forceinline__ void prep_sums(const T *iorlog, unsigned long long base, unsigned long long sy, unsigned long long sx, T sums[3])
+{
+    T v[DIM == 3 ? 3 : 1][3][3];
+#pragma unroll
+    for (int a = 0; a < (DIM == 3 ? 3 : 1); ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[a][b][c] = iorlog[base + a * sx + b * sy + c];
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax)
+    {
+        T sum = 0;
+#pragma unroll
+        for (int a = 0; a < (DIM == 3 ? 3 : 1); ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                {
+                    const int w = DIM == 3 ? stamp3_weight(ax, a, b, c) : stamp2_weight(ax, b, c);
+                    if (w != 0)
+                    {
+                        if constexpr (std::is_same<T, float>::value) sum = __fadd_rn(sum, __fmul_rn((float)w, v[a][b][c]));      // :284-287, not fused
+                        else sum = (T)((uint32_t)sum + (uint32_t)(w * v[a][b][c]));                                               // int32, wraps like the reference's
+                    }
+                }
+        sums[ax] = sum;
+    }
+}
+
+template <int DIM>
 __global__ void prep_f32_kernel(const PrepParams p, const float *iorlog, const uint32_t *translucency,
                                 float *volume, uint32_t *tr_cropped)
 {
     unsigned long long o, base, centre;
     if (!prep_index(p, o, base, centre)) return;
+    const unsigned long long sy = DIM == 3 ? p.ib[2] : p.ib[1], sx = DIM == 3 ? (unsigned long long)p.ib[1] * p.ib[2] : 0ull;
+    float sums[3];
+    prep_sums<float, DIM>(iorlog, base, sy, sx, sums);
     const float weight = 812.0f * 256.0f;                                  // image_util.cpp:438
     float out[4];
-    for (int ax = 0; ax < p.dim; ++ax)
-    {
-        float sum = 0.0f;
-        for (int j = 0; j < p.stamp[ax].n; ++j)                            // image_util.cpp:284-287: sum += w * in
-            sum = __fadd_rn(sum, __fmul_rn((float)p.stamp[ax].val[j], iorlog[base + p.stamp[ax].off[j]]));
-        out[ax] = __fdiv_rn(sum, weight);                                  // :288-291
-    }
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) out[ax] = __fdiv_rn(sums[ax], weight);       // :288-291
     const uint32_t tr = translucency[base + centre];
     tr_cropped[o] = tr;
-    out[p.dim] = (float)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);   // cu:654-659
-    float *dst = volume + o * (unsigned long long)(p.dim + 1);
-    if (p.dim == 3) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);      // one 16-byte store per voxel
-    else for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+    out[DIM] = (float)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);    // cu:654-659
+    float *dst = volume + o * (unsigned long long)(DIM + 1);
+    if (DIM == 3) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);      // one 16-byte store per voxel
+    else { dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; }
 }
 
 __device__ __forceinline__ int32_t div_round_closest(int32_t n, int32_t d) // image_util.h:34-38
@@ -98,28 +140,30 @@ __device__ __forceinline__ int32_t div_round_closest(int32_t n, int32_t d) // im
     return ((n < 0) ^ (d < 0)) ? ((n - d / 2) / d) : ((n + d / 2) / d);
 }
 
+template <int DIM>
 __global__ void prep_u32_kernel(const PrepParams p, const int32_t *iorlog, const uint32_t *translucency,
                                 int16_t *volume, uint32_t *tr_cropped, int *overflow)
 {
     unsigned long long o, base, centre;
     if (!prep_index(p, o, base, centre)) return;
+    const unsigned long long sy = DIM == 3 ? p.ib[2] : p.ib[1], sx = DIM == 3 ? (unsigned long long)p.ib[1] * p.ib[2] : 0ull;
+    int32_t sums[3];
+    prep_sums<int32_t, DIM>(iorlog, base, sy, sx, sums);
     const int32_t weight = 812 * 256;
     int16_t out[4];
-    for (int ax = 0; ax < p.dim; ++ax)
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax)
     {
-        uint32_t sum = 0;                                                  // int32 accumulate (wraps like the reference's)
-        for (int j = 0; j < p.stamp[ax].n; ++j)
-            sum += (uint32_t)(p.stamp[ax].val[j] * iorlog[base + p.stamp[ax].off[j]]);
-        const int32_t v = div_round_closest((int32_t)sum, weight);
+        const int32_t v = div_round_closest(sums[ax], weight);
         out[ax] = (int16_t)v;
         if ((int32_t)out[ax] != v) *overflow = 1;                          // "differention overflow" :293-296
     }
     const uint32_t tr = translucency[base + centre];
     tr_cropped[o] = tr;
-    out[p.dim] = (int16_t)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);
-    int16_t *dst = volume + o * (unsigned long long)(p.dim + 1);
-    if (p.dim == 3) *reinterpret_cast<short4 *>(dst) = make_short4(out[0], out[1], out[2], out[3]);
-    else for (int k = 0; k <= p.dim; ++k) dst[k] = out[k];
+    out[DIM] = (int16_t)((long long)(0x7FFFFFFFll - (long long)tr) / 0x10000ll);
+    int16_t *dst = volume + o * (unsigned long long)(DIM + 1);
+    if (DIM == 3) *reinterpret_cast<short4 *>(dst) = make_short4(out[0], out[1], out[2], out[3]);
+    else { dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; }
 }
 
 // TraceRaysCu ctor on planar inputs (cu:654-669): extra channel + interleave

@@ -80,9 +80,11 @@ enum {
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
     VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
-    VRT_OPT_REGION_LOG2   = 6,  /* 0 (default): single-launch marcher.  5..9: opt-in mode for INCOHERENT batches -- the volume is cut into
-                                   regions of 2^k voxels, rays are sorted by region and marched region by region so that the gathers are
-                                   served by L2 instead of DRAM (bit-identical results; 3-D, linear layout, no path output) */
+    VRT_OPT_REGION_LOG2   = 6,  /* region mode for INCOHERENT batches: the volume is cut into regions of 2^k voxels, rays are sorted by region
+                                   and marched region by region so that the gathers are served by L2 instead of DRAM (bit-identical results;
+                                   3-D, linear layout, no path output).  5..9: always, with that k.  -1: never.  0 (default): vrt_trace decides
+                                   per batch with a host-side coherence probe of the ray buffers (k = 6 when most neighbouring rays are not
+                                   neighbours in space and the volume exceeds L2); vrt_trace_device uses the single-launch marcher */
     VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 16) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */

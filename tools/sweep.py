@@ -97,6 +97,26 @@ def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
     sc.close()
 
 
+def cfg_c4h(size=512, nrays=8 << 20, iterations=4096):
+    """config 4 through the HOST call (vrt_trace): default options (coherence probe -> region mode) vs region mode disabled"""
+    ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
+    tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_random(nrays, 8.0, size - 9.0, 0x5EED0004)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    p_h = tpos.cpu().numpy().view(np.uint32).reshape(-1, 3); d_h = tdir.cpu().numpy().reshape(-1, 3)
+    ref_out = None
+    for name, region in (("auto", 0), ("off", -1), ("auto", 0), ("off", -1)):
+        sc.set_option(vrt.VRT_OPT_REGION_LOG2, region)
+        t0 = time.perf_counter(); out = sc.trace_rays_cu(p_h, d_h, [1, 1, 1], 0, iterations); dt = time.perf_counter() - t0
+        steps = int(out[2].astype(np.int64).sum())
+        same = True if ref_out is None else bool(all(np.array_equal(a, b) for a, b in zip(out[:4], ref_out[:4])))
+        ref_out = ref_out or out
+        print(json.dumps(dict(cfg="c4_hostcall", region=name, sec=round(dt, 4), grays=round(steps / dt / 1e9, 2), same_bits=same)), flush=True)
+    sc.close()
+
+
 def cfg_c3(size=512, nray=2048, iterations=4096):
     ior = W.ior_sines_torch(size, dev); tr = W.translucency_c3_torch(size, dev)
     sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
@@ -181,4 +201,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()
+        {"c4h": cfg_c4h, "c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()

@@ -538,7 +538,7 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_CHUNK_RAYS:     if (v < 0) return fail(VRT_ERR_INVALID, "chunk must be >= 0"); s->opt_chunk = v; break;
     case VRT_OPT_STEPS_PER_POLL: if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "steps per poll must be 1..4096"); s->opt_poll = v; break;
     case VRT_OPT_MAX_CTAS_PER_SM: if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "max CTAs per SM must be 0..32"); s->opt_max_ctas = v; break;
-    case VRT_OPT_REGION_LOG2:    if (v != 0 && (v < 5 || v > 9)) return fail(VRT_ERR_INVALID, "region log2 must be 0 or 5..9"); s->opt_region = v; break;
+    case VRT_OPT_REGION_LOG2:    if (v != 0 && v != -1 && (v < 5 || v > 9)) return fail(VRT_ERR_INVALID, "region log2 must be -1, 0 or 5..9"); s->opt_region = v; break;
     case VRT_OPT_REGION_ROUNDS:  if (v < 1 || v > 256) return fail(VRT_ERR_INVALID, "region rounds must be 1..256"); s->opt_rounds = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
@@ -649,9 +649,8 @@ static cudaError_t launch_region(const vrt_scene *s, const RegionParams &rp, cud
     return cudaGetLastError();
 }
 
-static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool di16, bool live, cudaStream_t st)
+static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool di16, bool live, cudaStream_t st, int k)
 {
-    const int k = (int)s->opt_region.load();
     const uint64_t n = mp.n;
     const uint32_t e = 1u << k;
     const uint32_t rx = (uint32_t)((s->bounds[0] + e - 1) / e), ry = (uint32_t)((s->bounds[1] + e - 1) / e), rz = (uint32_t)((s->bounds[2] + e - 1) / e);
@@ -724,7 +723,7 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
 // enqueue one marcher launch on `st`; `counter` is an 8-byte device scratch (zeroed here) or null for static mode
 static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
                          uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
-                         uint32_t *d_light, uint32_t *d_path, unsigned long long *counter, cudaStream_t st)
+                         uint32_t *d_light, uint32_t *d_path, unsigned long long *counter, cudaStream_t st, int region_log2)
 {
     if (n == 0) return VRT_OK;
     MarchParams p;
@@ -747,13 +746,40 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
-    if (s->opt_region.load() > 0 && s->dim == 3 && !path && !s->bricked && !s->tex)
-        return enqueue_march_regions(s, p, di16, live, st);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
+    if (region_log2 > 0 && s->dim == 3 && !path && !s->bricked && !s->tex)
+        return enqueue_march_regions(s, p, di16, live, st, region_log2);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
                                         : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
     VRT_CUDA(e);
     return VRT_OK;
+}
+
+// Host-side coherence probe for vrt_trace: are neighbouring rays of the batch neighbours in space?  Samples up to 4096 pairs
+// (i, i+1): a pair is incoherent when its start positions are more than 4 voxels apart or its directions differ by more than
+// ~25 degrees.  Coherent bundles (a camera, a parallel beam) keep the single-launch marcher; mostly incoherent batches over a
+// volume that does not fit L2 are marched in region mode (same results, DRAM traffic replaced by L2 hits).
+static bool batch_is_incoherent(uint64_t n, int dim, const uint32_t *pos, const void *dir, int dir_dtype)
+{
+    if (n < 2) return false;
+    const uint64_t samples = std::min<uint64_t>(n - 1, 4096);
+    uint64_t bad = 0;
+    for (uint64_t j = 0; j < samples; ++j)
+    {
+        const uint64_t i = ((j * 0x9E3779B97F4A7C15ull) >> 11) % (n - 1);      // scattered, not strided: a stride can alias with the row length of a ray grid
+        bool far = false;
+        double dot = 0, na = 0, nb = 0;
+        for (int d = 0; d < dim; ++d)
+        {
+            const int32_t dp = (int32_t)(pos[(i + 1) * dim + d] - pos[i * dim + d]);
+            if (dp > (4 << 16) || dp < -(4 << 16)) far = true;
+            const double a = dir_dtype == VRT_I16 ? (double)((const int16_t *)dir)[i * dim + d] : (double)((const float *)dir)[i * dim + d];
+            const double b = dir_dtype == VRT_I16 ? (double)((const int16_t *)dir)[(i + 1) * dim + d] : (double)((const float *)dir)[(i + 1) * dim + d];
+            dot += a * b; na += a * a; nb += b * b;
+        }
+        if (far || !(dot * dot >= 0.81 * na * nb && dot >= 0)) ++bad;
+    }
+    return bad * 2 > samples;
 }
 
 // Per host thread and device: the two pipeline streams of vrt_trace and a pinned/device staging pair for small
@@ -803,7 +829,8 @@ int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void
     unsigned long long *counter = nullptr;
     const bool refill = s->opt_refill.load() > 0 && s->dim == 3;
     if (refill) VRT_CUDA(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
-    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, counter, st);
+    const int region = (int)std::max<int64_t>(0, s->opt_region.load());      // device buffers: region mode only on request
+    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, counter, st, region);
     if (counter) cudaFreeAsync(counter, st);
     return rc;
 }
@@ -821,6 +848,12 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     const bool want_path = flags & VRT_TRACE_PATHS;
     const bool refill = s->opt_refill.load() > 0 && dim == 3;
     if (!t_ctx.ensure(s->device)) return fail(VRT_ERR_CUDA, "could not create the per-thread streams / staging buffers");
+    // region mode: on request (5..9), never (-1), or -- default 0 -- decided per batch by the host-side coherence probe
+    int region = (int)s->opt_region.load();
+    if (region == 0 && dim == 3 && !want_path && !s->bricked && !s->tex && n >= (1u << 18) &&
+        s->nvox * 4 * elem_size(s->store) > (96ull << 20) && batch_is_incoherent(n, dim, pos, dir, dir_dtype))
+        region = 6;
+    if (region < 0) region = 0;
 
     // Small batches (latency path): one packed H2D, one launch, one packed D2H through pinned staging -- 2 copies instead
     // of 6, no allocation.  Static ray-to-thread mapping (the grid covers the batch at once, nothing to refill).
@@ -835,7 +868,8 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             VRT_CUDA(cudaMemcpyAsync(d, h, b_pos + b_dir, cudaMemcpyHostToDevice, q));
             uint32_t *d_pos = (uint32_t *)d; void *d_dir = d + b_pos;
             uint32_t *d_eit = (uint32_t *)(d + b_pos + b_dir), *d_light = (uint32_t *)(d + b_pos + b_dir + b_u32);
-            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, nullptr, nullptr, q);
+            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, nullptr, nullptr, q,
+                               (int)std::max<int64_t>(0, s->opt_region.load()));
             if (rc) return rc;
             VRT_CUDA(cudaMemcpyAsync(h, d, b_pos + b_dir + 2 * b_u32, cudaMemcpyDeviceToHost, q));
             VRT_CUDA(cudaStreamSynchronize(q));
@@ -850,6 +884,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
     if (chunk == 0) chunk = n <= (1u << 19) ? n : std::max<uint64_t>(1u << 19, (n + 15) / 16);
+    if (region > 0 && s->opt_chunk.load() == 0) chunk = std::max<uint64_t>(chunk, std::min<uint64_t>(n, 4u << 20));   // regions want many rays per sort
     if (want_path)
     {
         const uint64_t per_ray = (uint64_t)iterations * dim * 4;
@@ -880,7 +915,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         {
             // results overwrite the start buffers on the device ("written back in place")
             int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, d_path,
-                                    refill ? (unsigned long long *)(buf + o_cnt) : nullptr, q);
+                                    refill ? (unsigned long long *)(buf + o_cnt) : nullptr, q, region);
             if (rc2) { result = rc2; }
         }
         if (result == VRT_OK)

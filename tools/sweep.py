@@ -97,6 +97,24 @@ def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
     sc.close()
 
 
+def cfg_c5h(size=1024, nray=4096, iterations=2048):
+    """config 5 through the HOST call with PAGEABLE buffers (numpy arrays, like the std::vectors of the reference API)"""
+    ior = W.ior_c5_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    del tr, ior
+    pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    p_h = tpos.cpu().numpy().view(np.uint32); d_h = tdir.cpu().numpy()
+    n = p_h.size // 3
+    epos = np.empty_like(p_h); edir = np.empty_like(d_h); eit = np.empty(n, np.uint32); light = np.empty(n, np.uint32)
+    for rep in range(4):
+        t0 = time.perf_counter(); sc.trace_host_buffers(p_h, d_h, [1, 1, 1], 0, iterations, epos, edir, eit, light); dt = time.perf_counter() - t0
+        steps = int(eit.astype(np.int64).sum())
+        print(json.dumps(dict(cfg="c5_hostcall_pageable", sec=round(dt, 4), grays=round(steps / dt / 1e9, 2))), flush=True)
+    sc.close()
+
+
 def cfg_c4h(size=512, nrays=8 << 20, iterations=4096):
     """config 4 through the HOST call (vrt_trace): default options (coherence probe -> region mode) vs region mode disabled"""
     ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
@@ -106,14 +124,19 @@ def cfg_c4h(size=512, nrays=8 << 20, iterations=4096):
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
     p_h = tpos.cpu().numpy().view(np.uint32).reshape(-1, 3); d_h = tdir.cpu().numpy().reshape(-1, 3)
+    n = p_h.shape[0]
+    outs = [np.zeros_like(p_h), np.zeros_like(d_h), np.zeros(n, np.uint32), np.zeros(n, np.uint32)]       # touched pages, like the caller's pre-sized vectors
     ref_out = None
-    for name, region in (("auto", 0), ("off", -1), ("auto", 0), ("off", -1)):
-        sc.set_option(vrt.VRT_OPT_REGION_LOG2, region)
-        t0 = time.perf_counter(); out = sc.trace_rays_cu(p_h, d_h, [1, 1, 1], 0, iterations); dt = time.perf_counter() - t0
-        steps = int(out[2].astype(np.int64).sum())
-        same = True if ref_out is None else bool(all(np.array_equal(a, b) for a, b in zip(out[:4], ref_out[:4])))
-        ref_out = ref_out or out
-        print(json.dumps(dict(cfg="c4_hostcall", region=name, sec=round(dt, 4), grays=round(steps / dt / 1e9, 2), same_bits=same)), flush=True)
+    combos = [("auto", 0, 0), ("off", -1, 0), ("auto", 0, 0), ("off", -1, 0)]
+    for c in os.environ.get("SWEEP_C4H", "").split(":"):
+        if c: combos.append(("forced",) + tuple(int(v) for v in c.split(",")))
+    for name, region, chunk in combos:
+        sc.set_option(vrt.VRT_OPT_REGION_LOG2, region); sc.set_option(vrt.VRT_OPT_CHUNK_RAYS, chunk)
+        t0 = time.perf_counter(); sc.trace_host_buffers(p_h, d_h, [1, 1, 1], 0, iterations, *outs); dt = time.perf_counter() - t0
+        steps = int(outs[2].astype(np.int64).sum())
+        same = True if ref_out is None else bool(all(np.array_equal(a, b) for a, b in zip(outs, ref_out)))
+        ref_out = ref_out or [o.copy() for o in outs]
+        print(json.dumps(dict(cfg="c4_hostcall", region=name, log2=region, chunk=chunk, sec=round(dt, 4), grays=round(steps / dt / 1e9, 2), same_bits=same)), flush=True)
     sc.close()
 
 
@@ -201,4 +224,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c4h": cfg_c4h, "c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()
+        {"c5h": cfg_c5h, "c4h": cfg_c4h, "c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()

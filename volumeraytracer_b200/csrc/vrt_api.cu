@@ -21,6 +21,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -789,7 +790,9 @@ struct ThreadCtx
 {
     static constexpr size_t kSmallBytes = 1u << 20;
     int device = -1;
-    cudaStream_t st[2] = {nullptr, nullptr};
+    static constexpr size_t kEvents = 128;
+    cudaStream_t st[2] = {nullptr, nullptr}, in = nullptr, out = nullptr;
+    cudaEvent_t ev[kEvents] = {};
     char *h_stage = nullptr;   // pinned
     char *d_stage = nullptr;
     bool ensure(int dev)
@@ -798,6 +801,10 @@ struct ThreadCtx
         release();
         if (cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
         if (cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+        if (cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+        if (cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+        for (size_t i = 0; i < kEvents; ++i)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); return false; }
         if (cudaMallocHost((void **)&h_stage, kSmallBytes) != cudaSuccess || cudaMalloc((void **)&d_stage, kSmallBytes) != cudaSuccess)
         { cudaGetLastError(); release(); return false; }
         device = dev;
@@ -806,6 +813,9 @@ struct ThreadCtx
     void release()
     {
         for (int i = 0; i < 2; ++i) if (st[i]) { cudaStreamDestroy(st[i]); st[i] = nullptr; }
+        if (in) { cudaStreamDestroy(in); in = nullptr; }
+        if (out) { cudaStreamDestroy(out); out = nullptr; }
+        for (size_t i = 0; i < kEvents; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
         if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; }
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         device = -1;
@@ -891,49 +901,81 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         const uint64_t cap = std::max<uint64_t>(1, (1ull << 31) / std::max<uint64_t>(per_ray, 1));     // <= 2 GiB of polyline per chunk
         chunk = std::min(chunk, cap);
     }
-    cudaStream_t st[2] = {t_ctx.st[0], t_ctx.st[1]};
-
+    // Four streams: `in` carries every H2D copy, st[0]/st[1] the marches of even/odd chunks, `out` every D2H copy, tied
+    // together by events.  All chunks are issued first (bounded by kWindowBytes / kWindowChunks of device memory), the D2H
+    // copies afterwards, oldest first.  With pinned host buffers everything is asynchronous and the copies of chunk i+1 /
+    // i-1 hide under the march of chunk i.  With PAGEABLE buffers (the std::vectors behind the reference API) the runtime
+    // makes a H2D copy wait for the stream it is issued on and blocks the host for the whole of a D2H copy: separate copy
+    // streams keep those waits off the marching streams, so the staging of later chunks and the read-back of earlier ones
+    // still overlap the march (config 5 through pageable numpy arrays: 171 -> see DESIGN.md section 5).
+    constexpr size_t kWindowBytes = 4ull << 30;
+    constexpr size_t kWindowChunks = ThreadCtx::kEvents / 2;
+    struct Pending { char *buf; uint64_t off, m; size_t o_dir, o_eit, o_light, o_path, b_path, bytes; cudaEvent_t marched; };
+    std::deque<Pending> pending;
+    size_t pending_bytes = 0;
     int result = VRT_OK;
-    int which = 0;
-    for (uint64_t off = 0; off < n && result == VRT_OK; off += chunk, which ^= 1)
-    {
-        const uint64_t m = std::min(chunk, n - off);
-        cudaStream_t q = st[which];
-        char *buf = nullptr;
-        // one stream-ordered allocation per chunk: [pos | dir | eit | light | counter | path]
-        const size_t b_pos = (size_t)m * dim * 4, b_dir = (size_t)m * dim * ds, b_u32 = (size_t)m * 4;
-        const size_t o_dir = (b_pos + 255) & ~(size_t)255, o_eit = (o_dir + b_dir + 255) & ~(size_t)255, o_light = (o_eit + b_u32 + 255) & ~(size_t)255;
-        const size_t o_cnt = (o_light + b_u32 + 255) & ~(size_t)255, o_path = o_cnt + 256;
-        const size_t b_path = want_path ? (size_t)m * iterations * dim * 4 : 0;
-        cudaError_t e = cudaMallocAsync((void **)&buf, o_path + b_path, q);
-        if (e != cudaSuccess) { result = fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); break; }
-        uint32_t *d_pos = (uint32_t *)buf; void *d_dir = buf + o_dir;
-        uint32_t *d_eit = (uint32_t *)(buf + o_eit), *d_light = (uint32_t *)(buf + o_light), *d_path = want_path ? (uint32_t *)(buf + o_path) : nullptr;
-        e = cudaMemcpyAsync(d_pos, pos + off * dim, b_pos, cudaMemcpyHostToDevice, q);
-        e = e == cudaSuccess ? cudaMemcpyAsync(d_dir, (const char *)dir + off * dim * ds, b_dir, cudaMemcpyHostToDevice, q) : e;
-        if (e == cudaSuccess)
-        {
-            // results overwrite the start buffers on the device ("written back in place")
-            int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, d_path,
-                                    refill ? (unsigned long long *)(buf + o_cnt) : nullptr, q, region);
-            if (rc2) { result = rc2; }
-        }
+    auto note = [&](cudaError_t e) {
+        if (e != cudaSuccess && result == VRT_OK) { result = fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
+    };
+    auto drain_front = [&]() {
+        Pending c = pending.front();
+        pending.pop_front();
+        pending_bytes -= c.bytes;
+        cudaStream_t q = t_ctx.out;
+        const size_t b_pos = (size_t)c.m * dim * 4, b_dir = (size_t)c.m * dim * ds, b_u32 = (size_t)c.m * 4;
+        note(cudaStreamWaitEvent(q, c.marched, 0));
         if (result == VRT_OK)
         {
-            e = e == cudaSuccess ? cudaMemcpyAsync(epos + off * dim, d_pos, b_pos, cudaMemcpyDeviceToHost, q) : e;
-            e = e == cudaSuccess ? cudaMemcpyAsync((char *)edir + off * dim * ds, d_dir, b_dir, cudaMemcpyDeviceToHost, q) : e;
-            e = e == cudaSuccess ? cudaMemcpyAsync(eit + off, d_eit, b_u32, cudaMemcpyDeviceToHost, q) : e;
-            e = e == cudaSuccess ? cudaMemcpyAsync(light + off, d_light, b_u32, cudaMemcpyDeviceToHost, q) : e;
-            if (want_path) e = e == cudaSuccess ? cudaMemcpyAsync(path + off * iterations * dim, d_path, b_path, cudaMemcpyDeviceToHost, q) : e;
+            note(cudaMemcpyAsync(epos + c.off * dim, c.buf, b_pos, cudaMemcpyDeviceToHost, q));
+            note(cudaMemcpyAsync((char *)edir + c.off * dim * ds, c.buf + c.o_dir, b_dir, cudaMemcpyDeviceToHost, q));
+            note(cudaMemcpyAsync(eit + c.off, c.buf + c.o_eit, b_u32, cudaMemcpyDeviceToHost, q));
+            note(cudaMemcpyAsync(light + c.off, c.buf + c.o_light, b_u32, cudaMemcpyDeviceToHost, q));
+            if (want_path) note(cudaMemcpyAsync(path + c.off * iterations * dim, c.buf + c.o_path, c.b_path, cudaMemcpyDeviceToHost, q));
         }
-        cudaFreeAsync(buf, q);
-        if (e != cudaSuccess && result == VRT_OK) { result = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
-    }
-    for (int i = 0; i < 2; ++i)
+        cudaFreeAsync(c.buf, q);
+    };
+
+    uint64_t index = 0;
+    for (uint64_t off = 0; off < n && result == VRT_OK; off += chunk, ++index)
     {
-        cudaError_t e = cudaStreamSynchronize(st[i]);
-        if (e != cudaSuccess && result == VRT_OK) { result = fail(VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
+        const uint64_t m = std::min(chunk, n - off);
+        cudaStream_t q = t_ctx.st[index & 1];
+        // one stream-ordered allocation per chunk: [pos | dir | eit | light | counter | path]
+        Pending c;
+        const size_t b_pos = (size_t)m * dim * 4, b_dir = (size_t)m * dim * ds, b_u32 = (size_t)m * 4;
+        c.off = off; c.m = m;
+        c.o_dir = (b_pos + 255) & ~(size_t)255; c.o_eit = (c.o_dir + b_dir + 255) & ~(size_t)255; c.o_light = (c.o_eit + b_u32 + 255) & ~(size_t)255;
+        const size_t o_cnt = (c.o_light + b_u32 + 255) & ~(size_t)255;
+        c.o_path = o_cnt + 256;
+        c.b_path = want_path ? (size_t)m * iterations * dim * 4 : 0;
+        c.bytes = c.o_path + c.b_path;
+        while (!pending.empty() && (pending_bytes + c.bytes > kWindowBytes || pending.size() >= kWindowChunks)) drain_front();
+        if (result != VRT_OK) break;
+        c.buf = nullptr;
+        note(cudaMallocAsync((void **)&c.buf, c.bytes, t_ctx.in));
+        if (result != VRT_OK) break;
+        cudaEvent_t staged = t_ctx.ev[(index * 2) % ThreadCtx::kEvents];
+        c.marched = t_ctx.ev[(index * 2 + 1) % ThreadCtx::kEvents];
+        note(cudaMemcpyAsync(c.buf, pos + off * dim, b_pos, cudaMemcpyHostToDevice, t_ctx.in));
+        note(cudaMemcpyAsync(c.buf + c.o_dir, (const char *)dir + off * dim * ds, b_dir, cudaMemcpyHostToDevice, t_ctx.in));
+        note(cudaEventRecord(staged, t_ctx.in));
+        note(cudaStreamWaitEvent(q, staged, 0));
+        if (result == VRT_OK)
+        {
+            // results overwrite the start buffers on the device ("written back in place")
+            uint32_t *d_pos = (uint32_t *)c.buf; void *d_dir = c.buf + c.o_dir;
+            int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, (uint32_t *)(c.buf + c.o_eit),
+                                    (uint32_t *)(c.buf + c.o_light), want_path ? (uint32_t *)(c.buf + c.o_path) : nullptr,
+                                    refill ? (unsigned long long *)(c.buf + o_cnt) : nullptr, q, region);
+            if (rc2 && result == VRT_OK) result = rc2;
+        }
+        note(cudaEventRecord(c.marched, q));
+        pending.push_back(c);
+        pending_bytes += c.bytes;
     }
+    while (!pending.empty()) drain_front();
+    cudaStream_t all[4] = {t_ctx.in, t_ctx.st[0], t_ctx.st[1], t_ctx.out};
+    for (cudaStream_t q : all) note(cudaStreamSynchronize(q));
     return result;
 }
 

@@ -736,6 +736,10 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.iterations = iterations; p.min_brightness = minb; p.n = n;
     p.pos = d_pos; p.dir = d_dir; p.epos = d_epos; p.edir = d_edir; p.eit = d_eit; p.light = d_light; p.path = d_path;
     p.steps_per_poll = (int)s->opt_poll.load();
+    {
+        const unsigned long long vb = (s->dim + 1) * elem_size(s->store);
+        p.row1 = (unsigned long long)p.bz * vb; p.row2 = (unsigned long long)(uint32_t)(p.by * p.bz) * vb; p.row3 = (unsigned long long)(uint32_t)((p.by + 1u) * p.bz) * vb;
+    }
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
     int kver = (int)s->opt_kernel.load();

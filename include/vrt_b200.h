@@ -85,7 +85,7 @@ enum {
                                    3-D, linear layout, no path output).  5..9: always, with that k.  -1: never.  0 (default): vrt_trace decides
                                    per batch with a host-side coherence probe of the ray buffers (k = 6 when most neighbouring rays are not
                                    neighbours in space and the volume exceeds L2); vrt_trace_device uses the single-launch marcher */
-    VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 16) */
+    VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 12) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
     VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an

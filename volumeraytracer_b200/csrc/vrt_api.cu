@@ -90,7 +90,7 @@ struct vrt_scene
     bool      owns_ior = false;
     int       num_sms = 148;
     // options
-    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{32}, opt_max_ctas{0}, opt_region{0}, opt_rounds{16};
+    std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -671,7 +671,9 @@ static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool
     RegionParams rp;
     rp.m = mp;
     rp.m.counter = (unsigned long long *)(ws + o_cnt);
-    rp.m.refill = std::max(1, (int)s->opt_refill.load());
+    // region rounds end ragged (rays suspend at different steps): refill early and poll often, unlike the single-launch marcher
+    rp.m.refill = std::min(8, std::max(1, (int)s->opt_refill.load()));
+    rp.m.steps_per_poll = std::min(32, mp.steps_per_poll);
     rp.st_pos = (uint32_t *)(ws + o_pos); rp.st_dir = (float *)(ws + o_dir); rp.st_it = (uint32_t *)(ws + o_it); rp.st_light = (uint32_t *)(ws + o_light);
     rp.log2_edge = k; rp.margin = std::min<uint32_t>(8u, e / 4); rp.ry = ry; rp.rz = rz;
     uint16_t *keys[2] = {(uint16_t *)(ws + o_k0), (uint16_t *)(ws + o_k1)};

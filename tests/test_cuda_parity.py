@@ -568,6 +568,46 @@ def test_randomised_configurations(vrt, oracle):
         t.close()
 
 
+def test_channel3_edge_values_and_degenerate_directions(vrt, oracle):
+    """The default kernel skips channel 3 in cells whose 8 corners all carry its sign bit and re-derives the reason for
+    leaving the step loop afterwards.  Volumes whose channel 3 mixes negative values, -0.0, +0.0, denormal / tiny positives and
+    NaN in small blobs (so clear cells, opaque cells and mixed cells all occur), gradients with infinities, and rays with zero,
+    huge, denormal, infinite and NaN direction components must all come out exactly as the oracle computes them."""
+    rng = np.random.default_rng(77)
+    shape = (23, 19, 21)
+    nvox = int(np.prod(shape))
+    vol = np.zeros((nvox, 4), np.float32)
+    vol[:, :3] = rng.normal(0, 3000.0, size=(nvox, 3)).astype(np.float32)      # bends a unit direction (65536 internally) noticeably per step
+    choices = np.array([-32768.0, -1.0, -0.0, 0.0, 1e-40, 1e-30, 5.0, 32767.0, np.nan], np.float32)
+    blob = rng.integers(0, len(choices), size=tuple((np.array(shape) + 3) // 4))
+    blob[rng.random(blob.shape) < 0.7] = 0                                      # mostly clear
+    c3 = choices[np.kron(blob, np.ones((4, 4, 4), np.int64))[:shape[0], :shape[1], :shape[2]]]
+    c3.view(np.uint32)[np.isnan(c3) & (rng.random(shape) < 0.5)] |= np.uint32(0x80000000)   # NaNs of either sign
+    vol[:, 3] = c3.reshape(-1)
+    vol[rng.integers(0, nvox, 5), rng.integers(0, 3, 5)] = np.inf
+    tr = np.full(nvox, 0xFFFFFFFF, np.uint32)
+    n = 6000
+    pos = (rng.random((n, 3)) * (np.array(shape) - 1.0) * 65536.0).astype(np.uint32)
+    d = rng.normal(0, 1.2, size=(n, 3)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-45, 1e-38, 1e30, 3e38, np.inf, -np.inf, np.nan], np.float32)
+    rows = rng.integers(0, n, 600)
+    d[rows, rng.integers(0, 3, 600)] = special[rng.integers(0, len(special), 600)]
+    d[rows[:60]] = 0.0
+    for isc, iters in (([1.0, 1.0, 1.0], 300), ([0.5, 2.0, 1.25], 77)):
+        want = oracle.trace(vol, shape, pos, d, isc, iters, round_mode=oracle.ROUND_DEVICE)
+        t = vrt.TraceRaysCu.from_interleaved(shape, vol, tr)
+        for kernel, refill, poll in ((0, 32, 128), (3, 1, 1), (3, 0, 7), (2, 32, 32), (1, 8, 500), (6, 32, 32)):
+            t.set_option(vrt.VRT_OPT_KERNEL, kernel); t.set_option(vrt.VRT_OPT_REFILL, refill); t.set_option(vrt.VRT_OPT_STEPS_PER_POLL, poll)
+            got = t.trace_rays_cu(pos, d, isc, 0, iters)
+            for g, w, nme in zip(got[:3], want[:3], ("end_position", "end_direction", "end_iteration")):
+                g = np.ascontiguousarray(g).reshape(-1).view(np.uint32).copy(); w = np.ascontiguousarray(w).reshape(-1).view(np.uint32).copy()
+                if nme == "end_direction":      # NaN payloads are unspecified (x86 keeps an operand's payload, the GPU returns the canonical NaN)
+                    g[np.isnan(g.view(np.float32))] = 0x7FC00000; w[np.isnan(w.view(np.float32))] = 0x7FC00000
+                bad = np.flatnonzero(g != w)
+                assert bad.size == 0, "kernel %d refill %d poll %d: %s differs at %s: %s vs %s" % (kernel, refill, poll, nme, bad[:5], g[bad[:5]], w[bad[:5]])
+        t.close()
+
+
 @pytest.mark.parametrize("volk", ["f32", "i16"])
 def test_texture_layout_is_bit_identical(vrt, oracle, volk):
     """VRT_SCENE_LAYOUT_TEXTURE: corners point-sampled from a block-linear CUDA 3-D array -- same bits out."""

@@ -568,6 +568,15 @@ def test_randomised_configurations(vrt, oracle):
         t.close()
 
 
+def test_short_division_sequence_is_exact_over_its_whole_range(vrt):
+    """The fast loop divides 0x42000000p0f by |dir|^2 with a reciprocal + 5 FMA sequence instead of div.rn.f32 (cu:346); the
+    device self-test compares the two for every float the sequence is used for (1.6e9 values)."""
+    import ctypes as C
+    bad = C.c_uint64(12345)
+    assert vrt.lib().vrt_selftest_division(0, C.byref(bad)) == 0
+    assert bad.value == 0
+
+
 def test_channel3_edge_values_and_degenerate_directions(vrt, oracle):
     """The default kernel skips channel 3 in cells whose 8 corners all carry its sign bit and re-derives the reason for
     leaving the step loop afterwards.  Volumes whose channel 3 mixes negative values, -0.0, +0.0, denormal / tiny positives and

@@ -24,7 +24,7 @@ SYMBOLS = [
     "vrt_last_error", "vrt_version", "vrt_device_count", "vrt_scene_create", "vrt_scene_create_interleaved",
     "vrt_scene_create_device", "vrt_scene_create_from_ior", "vrt_scene_destroy", "vrt_scene_info",
     "vrt_scene_download", "vrt_scene_export_device", "vrt_scene_set_option", "vrt_scene_get_option", "vrt_trace", "vrt_trace_device",
-    "vrt_normalise_rays_device", "vrt_measure_gather_bandwidth", "vrt_launch_count",
+    "vrt_normalise_rays_device", "vrt_measure_gather_bandwidth", "vrt_selftest_division", "vrt_launch_count",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
         L.vrt_trace_device.argtypes = [vp, u64, vp, vp, i32, vp, u32, u32, C.c_uint, vp, vp, vp, vp, vp, vp]
         L.vrt_normalise_rays_device.argtypes = [vp, u64, vp, vp, i32, C.POINTER(C.c_int64), vp]
         L.vrt_measure_gather_bandwidth.argtypes = [i32, u64, i32, i32, C.POINTER(C.c_double)]
+        L.vrt_selftest_division.argtypes = [i32, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 

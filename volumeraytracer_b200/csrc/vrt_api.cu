@@ -1020,6 +1020,25 @@ int vrt_normalise_rays_device(vrt_scene *s, uint64_t n, uint32_t *d_pos, void *d
     return VRT_OK;
 }
 
+int vrt_selftest_division(int device, uint64_t *mismatches)
+{
+    if (!mismatches) return fail(VRT_ERR_INVALID, "mismatches is null");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    unsigned long long *d_bad = nullptr, h_bad = 0;
+    VRT_CUDA(cudaMalloc((void **)&d_bad, 8));
+    VRT_CUDA(cudaMemset(d_bad, 0, 8));
+    // every bit pattern div_is_fast() accepts: [0x10000000, 0x70000000), plus a margin on both sides that it must reject
+    div_selftest_kernel<0><<<148 * 8, 256>>>(0x0F000000u, 0x62000000u, d_bad);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    VRT_CUDA(e);
+    *mismatches = h_bad;
+    return VRT_OK;
+}
+
 int vrt_measure_gather_bandwidth(int device, uint64_t bytes, int sector_bytes, int iters, double *gb_per_s)
 {
     if (!gb_per_s || (sector_bytes != 16 && sector_bytes != 32) || bytes < 4096 || iters < 1) return fail(VRT_ERR_INVALID, "bad arguments");

@@ -69,7 +69,12 @@ enum {
     /* layout study: additionally stage the (float) volume in a CUDA 3-D array (block-linear tiling) and fetch the corners
      * through a point-sampled float4 texture object; filtering stays in software (hardware trilinear has 8-bit weights, the
      * reference uses 16).  3-D only, no path output; results bit-identical.  Not with VRT_SCENE_BORROW / _KEEP_I16 / _BRICK. */
-    VRT_SCENE_LAYOUT_TEXTURE = 1u << 3
+    VRT_SCENE_LAYOUT_TEXTURE = 1u << 3,
+    /* layout study: store, for every cell, the voxel and its z neighbour side by side (32 bytes per cell, float scenes, 3-D):
+     * the two z-adjacent corners of a row become one aligned 256-bit load, a cell change 4 loads / 4 sectors instead of 8
+     * loads / ~6 sectors, at twice the device memory.  Results bit-identical; works with path output, live translucency and
+     * region mode.  Not with VRT_SCENE_BORROW / _KEEP_I16 / _BRICK / _TEXTURE. */
+    VRT_SCENE_LAYOUT_PAIR = 1u << 4
 };
 
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */

@@ -16,6 +16,7 @@ dev = torch.device("cuda", 0)
 BRICK = bool(int(os.environ.get("SWEEP_BRICK", "0")))
 KEEP16 = bool(int(os.environ.get("SWEEP_KEEP_I16", "0")))
 TEX = bool(int(os.environ.get("SWEEP_TEXTURE", "0")))
+PAIR = bool(int(os.environ.get("SWEEP_PAIR", "0")))
 
 
 def timed(fn, reps=2):
@@ -40,7 +41,7 @@ def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
         co.set_option(vrt.VRT_OPT_MAX_CTAS_PER_SM, ctas)
         t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
         steps = int(out[2].to(torch.int64).sum().item())
-        print(json.dumps(dict(cfg=name + ("_brick" if BRICK else "") + ("_tex" if TEX else ""), kver=kver, block=block, refill=refill, poll=poll, ctas=ctas, region=region, sec=round(t, 4), steps=steps,
+        print(json.dumps(dict(cfg=name + ("_brick" if BRICK else "") + ("_tex" if TEX else "") + ("_pair" if PAIR else ""), kver=kver, block=block, refill=refill, poll=poll, ctas=ctas, region=region, sec=round(t, 4), steps=steps,
                               grays=round(steps / t / 1e9, 2))), flush=True)
         res.append((steps / t / 1e9, kver, block, refill, poll))
     return res
@@ -59,7 +60,7 @@ VARIANTS = _env_variants() or [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (
 
 def cfg_c5(size=1024, nray=4096, iterations=2048):
     ior = W.ior_c5_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
-    t0 = time.time(); sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
+    t0 = time.time(); sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX, paired=PAIR); torch.cuda.synchronize()
     print("c5 scene prep %.2fs, volume %.2f GB" % (time.time() - t0, sc.volume_bytes / 1e9), flush=True)
     del tr
     pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
@@ -76,7 +77,7 @@ def cfg_c5i(size=1024, nray=4096, iterations=2048):
     ior_u = torch.where(ior_u >= (1 << 31), ior_u - (1 << 32), ior_u).to(torch.int32)
     del ior
     tr = W.clear_translucency_torch((size,) * 3, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior_u, tr, bricked=BRICK, keep_i16=KEEP16); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior_u, tr, bricked=BRICK, keep_i16=KEEP16, paired=PAIR); torch.cuda.synchronize()
     print("c5 int16 scene, volume %.2f GB" % (sc.volume_bytes / 1e9), flush=True)
     del tr
     pos, d = W.rays_parallel_x(nray, nray, 2.0, size - 3.0, x0=2.0)
@@ -89,7 +90,7 @@ def cfg_c5i(size=1024, nray=4096, iterations=2048):
 def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
     ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
     tr = W.clear_translucency_torch((size,) * 3, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX, paired=PAIR); torch.cuda.synchronize()
     pos, d = W.rays_random(nrays, 8.0, size - 9.0, 0x5EED0004)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
@@ -142,7 +143,7 @@ def cfg_c4h(size=512, nrays=8 << 20, iterations=4096):
 
 def cfg_c3(size=512, nray=2048, iterations=4096):
     ior = W.ior_sines_torch(size, dev); tr = W.translucency_c3_torch(size, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX, paired=PAIR); torch.cuda.synchronize()
     pos, d = W.rays_parallel_x(nray, nray, 4.0, size - 5.0, x0=2.0)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
@@ -163,7 +164,7 @@ def cfg_c1(size=64, nray=64, iterations=1024, reps=64):
 
 def cfg_c2(size=256, nray=1024, iterations=4096, with_ref=False):
     ior = W.ior_luneburg_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
-    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX); torch.cuda.synchronize()
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX, paired=PAIR); torch.cuda.synchronize()
     pos, d = W.rays_parallel_x(nray, nray, 30.0, 225.0, x0=2.0)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)

@@ -79,6 +79,7 @@ struct vrt_scene
     uint32_t *d_translucency = nullptr;
     bool      owns = true;
     bool      bricked = false;     // VRT_SCENE_LAYOUT_BRICK
+    bool      paired = false;      // VRT_SCENE_LAYOUT_PAIR: d_volume holds {voxel, z neighbour} per cell (2 x nvox float4)
     double    flat_fraction = 0.0; // share of voxels with zero gradient and non-positive extra channel (set by apply_storage)
     cudaArray_t tex_array = nullptr;   // VRT_SCENE_LAYOUT_TEXTURE: block-linear copy + point-sampled texture object
     cudaTextureObject_t tex = 0;
@@ -249,6 +250,23 @@ static int apply_storage(vrt_scene *s, unsigned flags)
         VRT_CUDA(cudaCreateTextureObject(&s->tex, &rd, &td, nullptr));
         return VRT_OK;
     }
+    if (flags & VRT_SCENE_LAYOUT_PAIR)
+    {
+        if (s->dim != 3 || s->store != VRT_F32 || !s->owns || (flags & VRT_SCENE_LAYOUT_BRICK))
+            return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_PAIR needs a 3-D scene staged as float and excludes VRT_SCENE_LAYOUT_BRICK / _TEXTURE / _KEEP_I16 / _BORROW");
+        void *dst = nullptr;
+        cudaError_t e = cudaMalloc(&dst, s->nvox * 32ull);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(VRT_ERR_NOMEM, "not enough device memory for the pair layout"); }
+        pair_convert_kernel<<<(unsigned)((s->nvox + 255) / 256), 256>>>((const float4 *)s->d_volume, (float4 *)dst, s->nvox);
+        ++g_launches;
+        e = cudaGetLastError();
+        e = e == cudaSuccess ? cudaDeviceSynchronize() : e;
+        if (e != cudaSuccess) { cudaFree(dst); cudaGetLastError(); return fail(VRT_ERR_CUDA, cudaGetErrorString(e)); }
+        cudaFree(s->d_volume);
+        s->d_volume = dst;
+        s->paired = true;
+        return VRT_OK;
+    }
     if (!(flags & VRT_SCENE_LAYOUT_BRICK)) return VRT_OK;
     if (s->dim != 3) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK is 3-D only");
     if (!s->owns) return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_BRICK cannot be combined with VRT_SCENE_BORROW");
@@ -271,6 +289,21 @@ static int linearise(const vrt_scene *s, void *d_out, cudaStream_t st)
 {
     const unsigned long long nelem = s->nvox * (unsigned long long)(s->dim + 1);
     const bool narrow = s->store != s->dtype;
+    if (s->paired)      // first voxel of every pair: a strided copy
+    {
+        void *lin = d_out;
+        if (narrow) VRT_CUDA(cudaMallocAsync(&lin, nelem * 4, st));
+        cudaError_t e = cudaMemcpy2DAsync(lin, 16, s->d_volume, 32, 16, s->nvox, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && narrow)
+        {
+            narrow_f32_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>((const float *)lin, (short *)d_out, nelem);
+            ++g_launches;
+            e = cudaGetLastError();
+        }
+        if (narrow) cudaFreeAsync(lin, st);
+        VRT_CUDA(e);
+        return VRT_OK;
+    }
     if (!s->bricked && !narrow)
     {
         VRT_CUDA(cudaMemcpyAsync(d_out, s->d_volume, nelem * elem_size(s->dtype), cudaMemcpyDeviceToDevice, st));
@@ -503,7 +536,7 @@ int vrt_scene_download(const vrt_scene *s, void *host_volume, uint32_t *host_tra
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     DeviceGuard g(s->device);
     const size_t bytes = s->nvox * (s->dim + 1) * elem_size(s->dtype);
-    if (host_volume && (s->bricked || s->store != s->dtype))      // hand out the reference's layout and element type
+    if (host_volume && (s->bricked || s->paired || s->store != s->dtype))      // hand out the reference's layout and element type
     {
         void *tmp = nullptr;
         VRT_CUDA(cudaMalloc(&tmp, bytes));
@@ -598,7 +631,8 @@ static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, 
 template <typename VoxT, bool DIR_I16, bool LIVE>
 static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path, int kver, int block, cudaStream_t st)
 {
-    if (path) return launch3<VoxT, DIR_I16, LIVE, true, 2>(s, p, block, st);   // polyline output is store-bound: one variant
+    if (path) return kver == 7 ? launch3<VoxT, DIR_I16, LIVE, true, 7>(s, p, block, st)
+                               : launch3<VoxT, DIR_I16, LIVE, true, 2>(s, p, block, st);   // polyline output is store-bound: one variant per layout
     switch (kver)
     {
     case 1: return launch3<VoxT, DIR_I16, LIVE, false, 1>(s, p, block, st);
@@ -606,6 +640,7 @@ static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path
     case 4: return launch3<VoxT, DIR_I16, LIVE, false, 4>(s, p, block, st);
     case 5: return launch3<VoxT, DIR_I16, LIVE, false, 5>(s, p, block, st);
     case 6: return launch3<VoxT, DIR_I16, LIVE, false, 6>(s, p, block, st);
+    case 7: return launch3<VoxT, DIR_I16, LIVE, false, 7>(s, p, block, st);
     default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
     }
 }
@@ -739,9 +774,10 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.pos = d_pos; p.dir = d_dir; p.epos = d_epos; p.edir = d_edir; p.eit = d_eit; p.light = d_light; p.path = d_path;
     p.steps_per_poll = (int)s->opt_poll.load();
     {
-        const unsigned long long vb = (s->dim + 1) * elem_size(s->store);
+        const unsigned long long vb = s->paired ? 32ull : (s->dim + 1) * elem_size(s->store);
         p.row1 = (unsigned long long)p.bz * vb; p.row2 = (unsigned long long)(uint32_t)(p.by * p.bz) * vb; p.row3 = (unsigned long long)(uint32_t)((p.by + 1u) * p.bz) * vb;
     }
+    p.pair = s->paired ? 1 : 0;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
     int kver = (int)s->opt_kernel.load();
@@ -749,6 +785,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
                                // (config 1: 25x, config 2: +7 %) and loses where flat and curved cells mix inside a warp
     if (s->bricked) kver = 4;
     if (s->tex) kver = 5;
+    if (s->paired) kver = 7;
     p.tex = s->tex;
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();

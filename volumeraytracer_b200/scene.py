@@ -34,7 +34,7 @@ class Options:
 class TraceRaysCu:
     """B200 drop-in for TraceRaysCu<DiffType> (DiffType from the planes' dtype: float32 or int16)."""
 
-    def __init__(self, output_sizes, diff, translucency_cropped, device=0, _handle=None, bricked=False, keep_i16=False, texture=False):
+    def __init__(self, output_sizes, diff, translucency_cropped, device=0, _handle=None, bricked=False, keep_i16=False, texture=False, paired=False):
         self._h = C.c_void_p()
         self._keepalive = None
         if _handle is not None:
@@ -54,7 +54,7 @@ class TraceRaysCu:
                 raise ValueError("imagesizes doesn't match")
             ptrs = (C.c_void_p * dim)(*[p.ctypes.data for p in planes])
             L.check(L.lib().vrt_scene_create(C.byref(self._h), device, dim, _p(bounds), dt, ptrs, _p(tr),
-                                             (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0)))
+                                             (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0) | (L.VRT_SCENE_LAYOUT_PAIR if paired else 0)))
         self._read_info()
 
     # -- alternative constructors -------------------------------------------------------------------
@@ -83,7 +83,7 @@ class TraceRaysCu:
         return obj
 
     @classmethod
-    def from_ior(cls, bound_vec, ior, translucency, device=0, bricked=False, keep_i16=False, texture=False):
+    def from_ior(cls, bound_vec, ior, translucency, device=0, bricked=False, keep_i16=False, texture=False, paired=False):
         """GPU scene prep (f1).  ior: numpy float32|uint32 or a torch CUDA tensor of those; bounds UNCROPPED."""
         bounds = np.asarray(bound_vec, dtype=np.uint64)
         h = C.c_void_p()
@@ -93,13 +93,13 @@ class TraceRaysCu:
             if ior.size != int(np.prod(bounds.astype(object))) or tr.size != ior.size:
                 raise VrtErrorCompat("imagesizes doesn't match")
             L.check(L.lib().vrt_scene_create_from_ior(C.byref(h), device, len(bounds), _p(bounds), _DT[ior.dtype], _p(ior), _p(tr), 0,
-                                                      (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0)))
+                                                      (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0) | (L.VRT_SCENE_LAYOUT_PAIR if paired else 0)))
         else:
             import torch
             dt = L.VRT_F32 if ior.dtype == torch.float32 else L.VRT_U32
             L.check(L.lib().vrt_scene_create_from_ior(C.byref(h), ior.device.index or 0, len(bounds), _p(bounds), dt,
                                                       C.c_void_p(ior.data_ptr()), C.c_void_p(translucency.data_ptr()), 1,
-                                                      (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0)))
+                                                      (L.VRT_SCENE_LAYOUT_BRICK if bricked else 0) | (L.VRT_SCENE_KEEP_I16 if keep_i16 else 0) | (L.VRT_SCENE_LAYOUT_TEXTURE if texture else 0) | (L.VRT_SCENE_LAYOUT_PAIR if paired else 0)))
         return cls(None, None, None, _handle=h)
 
     # -- plumbing -----------------------------------------------------------------------------------

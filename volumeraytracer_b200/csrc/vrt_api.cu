@@ -791,7 +791,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
-    if (kver == 3 && !live && !path && p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f) kver = 9;   // unit invscale: two multiplies fewer per step, same bits
+    if (kver == 3 && !path && p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f) kver = 9;   // unit invscale: two multiplies fewer per step, same bits
     if (region_log2 > 0 && s->dim == 3 && !path && !s->bricked && !s->tex)
         return enqueue_march_regions(s, p, di16, live, st, region_log2);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));

@@ -779,6 +779,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
         p.row1 = (unsigned long long)p.bz * vb; p.row2 = (unsigned long long)(uint32_t)(p.by * p.bz) * vb; p.row3 = (unsigned long long)(uint32_t)((p.by + 1u) * p.bz) * vb;
     }
     p.pair = s->paired ? 1 : 0;
+    p.one[0] = p.one[1] = 1.0f;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
     int kver = (int)s->opt_kernel.load();

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128, 5) march3_region_kernel(const RegionParam
             }
             unsigned long long gxy, gzw;
             float gz, gw, sx, sy;
-            trilerp_packed(q, px, py, pz, gxy, gzw);                                             // cu:342
+            trilerp_packed(q, px, py, pz, gxy, gzw, scale48_const());                            // cu:342
             unpack2(gzw, gz, gw);
             if (gw > 0.0f) { done = true; it_final = it + 1u; break; }                           // cu:343
             unsigned long long dxy = fma2(pack2(invx, invy), gxy, pack2(dx, dy));                // cu:344-345

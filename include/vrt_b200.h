@@ -170,9 +170,11 @@ VRT_API int vrt_normalise_rays_device(vrt_scene *scene, uint64_t n_rays, uint32_
  * random 32-byte-sector gather over a `bytes`-sized device buffer (L2 resident when bytes << L2 size), returns GB/s. */
 VRT_API int vrt_measure_gather_bandwidth(int device, uint64_t bytes, int sector_bytes, int iters, double *gb_per_s);
 
-/* Device self-test of the marcher's short division sequence: compares it with IEEE division (div.rn.f32) of the reference's
-   constant 0x42000000p0f (cu:346) by EVERY float for which the marcher uses it (2^-95 <= d < 2^97, 1.6e9 values) and returns
-   the number of differing results in *mismatches (must be 0). */
+/* Device self-test of the marcher's two exact shortcuts, each over its WHOLE input range: the short division sequence against
+   IEEE division (div.rn.f32) of the reference's constant 0x42000000p0f (cu:346) by every float for which the marcher uses it
+   (2^-95 <= d < 2^97, 1.6e9 values), and the add-a-constant float-to-integer rounding of the unit-invscale kernels against
+   cvt.rni.s32.f32 (cu:347) for every float of magnitude below 2^22 (2.5e9 values).  *mismatches = number of differing results
+   (must be 0). */
 VRT_API int vrt_selftest_division(int device, uint64_t *mismatches);
 
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */

@@ -569,8 +569,9 @@ def test_randomised_configurations(vrt, oracle):
 
 
 def test_short_division_sequence_is_exact_over_its_whole_range(vrt):
-    """The fast loop divides 0x42000000p0f by |dir|^2 with a reciprocal + 5 FMA sequence instead of div.rn.f32 (cu:346); the
-    device self-test compares the two for every float the sequence is used for (1.6e9 values)."""
+    """The fast loop divides 0x42000000p0f by |dir|^2 with a reciprocal + 5 FMA sequence instead of div.rn.f32 (cu:346) and, with
+    unit invscale, rounds the step to an integer by adding 1.5 * 2^23 instead of cvt.rni (cu:347); the device self-test compares
+    each shortcut with the instruction it replaces for every float it is used for (1.6e9 + 2.5e9 values)."""
     import ctypes as C
     bad = C.c_uint64(12345)
     assert vrt.lib().vrt_selftest_division(0, C.byref(bad)) == 0

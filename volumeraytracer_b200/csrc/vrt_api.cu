@@ -1070,7 +1070,10 @@ int vrt_selftest_division(int device, uint64_t *mismatches)
     VRT_CUDA(cudaMemset(d_bad, 0, 8));
     // every bit pattern div_is_fast() accepts: [0x10000000, 0x70000000), plus a margin on both sides that it must reject
     div_selftest_kernel<0><<<148 * 8, 256>>>(0x0F000000u, 0x62000000u, d_bad);
-    ++g_launches;
+    // rni_small(): every float with |v| < 2^22 (bit patterns below 0x4A800000, both signs)
+    rni_selftest_kernel<<<148 * 8, 256>>>(0x00000000u, 0x4A800000u, d_bad);
+    rni_selftest_kernel<<<148 * 8, 256>>>(0x80000000u, 0x4A800000u, d_bad);
+    g_launches += 3;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost);
     cudaFree(d_bad);

@@ -595,7 +595,7 @@ def test_channel3_edge_values_and_degenerate_directions(vrt, oracle):
     c3.view(np.uint32)[np.isnan(c3) & (rng.random(shape) < 0.5)] |= np.uint32(0x80000000)   # NaNs of either sign
     vol[:, 3] = c3.reshape(-1)
     vol[rng.integers(0, nvox, 5), rng.integers(0, 3, 5)] = np.inf
-    tr = np.full(nvox, 0xFFFFFFFF, np.uint32)
+    tr = (np.uint32(0xFFFFFFFF) - rng.integers(0, 1 << 25, nvox).astype(np.uint32)).astype(np.uint32)   # only read by the live runs below
     n = 6000
     pos = (rng.random((n, 3)) * (np.array(shape) - 1.0) * 65536.0).astype(np.uint32)
     d = rng.normal(0, 1.2, size=(n, 3)).astype(np.float32)
@@ -615,6 +615,17 @@ def test_channel3_edge_values_and_degenerate_directions(vrt, oracle):
                     g[np.isnan(g.view(np.float32))] = 0x7FC00000; w[np.isnan(w.view(np.float32))] = 0x7FC00000
                 bad = np.flatnonzero(g != w)
                 assert bad.size == 0, "kernel %d refill %d poll %d: %s differs at %s: %s vs %s" % (kernel, refill, poll, nme, bad[:5], g[bad[:5]], w[bad[:5]])
+        # the same with the translucency plane live (fast loop of the unit-invscale kernel / generic loop otherwise)
+        wantl = oracle.trace(vol, shape, pos, d, isc, iters, translucency=tr, min_brightness=0xC0000000, round_mode=oracle.ROUND_DEVICE)
+        for kernel, refill, poll in ((0, 32, 128), (3, 1, 1), (2, 0, 9)):
+            t.set_option(vrt.VRT_OPT_KERNEL, kernel); t.set_option(vrt.VRT_OPT_REFILL, refill); t.set_option(vrt.VRT_OPT_STEPS_PER_POLL, poll)
+            got = t.trace_rays_cu(pos, d, isc, 0xC0000000, iters, live_translucency=True)
+            for g, w, nme in zip(got[:4], wantl[:4], ("end_position", "end_direction", "end_iteration", "remaining_light")):
+                g = np.ascontiguousarray(g).reshape(-1).view(np.uint32).copy(); w = np.ascontiguousarray(w).reshape(-1).view(np.uint32).copy()
+                if nme == "end_direction":
+                    g[np.isnan(g.view(np.float32))] = 0x7FC00000; w[np.isnan(w.view(np.float32))] = 0x7FC00000
+                bad = np.flatnonzero(g != w)
+                assert bad.size == 0, "live kernel %d refill %d poll %d: %s differs at %s: %s vs %s" % (kernel, refill, poll, nme, bad[:5], g[bad[:5]], w[bad[:5]])
         t.close()
 
 

@@ -81,3 +81,19 @@ def test_error_behaviour_mirrors_the_reference():
         vrt.RaytraceScene([5, 5, 5, 5], np.ones(625, np.float32), np.zeros(625, np.uint32))
     with pytest.raises(TypeError):
         vrt.TraceRaysCu([4, 4, 4], [np.zeros(64, np.float64)] * 3, np.zeros(64, np.uint32))
+
+
+def test_python_constants_match_the_header():
+    """Every enumerator of include/vrt_b200.h that the ctypes module mirrors has the same value there."""
+    import re
+    from volumeraytracer_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "vrt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    seen = 0
+    for name, expr in re.findall(r"\b(VRT_[A-Z0-9_]+)\s*=\s*([^,}\n]+)", text):
+        expr = expr.strip().replace("u", "")
+        value = eval(expr, {"__builtins__": {}})           # "1 << 3", "-2", "100"
+        if hasattr(_lib, name):
+            assert getattr(_lib, name) == value, "%s: header %r, _lib.py %r" % (name, value, getattr(_lib, name))
+            seen += 1
+    assert seen >= 20

@@ -80,7 +80,9 @@ enum {
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */
 enum {
     VRT_OPT_KERNEL        = 0,  /* 0 default (= 3), 1 reference-like (reload every step), 2 register cell cache, 3 cell cache + packed
-                                   f32x2, 6 = 3 + empty-space fast path (opt-in: coherent bundles through mostly empty volumes) */
+                                   f32x2 + fast loop for cells without a possibly opaque corner (with invscale == (1,1,1) its
+                                   unit-invscale variant is launched: same bits, fewer instructions), 6 = 3 + empty-space fast path
+                                   (opt-in: coherent bundles through mostly empty volumes) */
     VRT_OPT_BLOCK_THREADS = 1,  /* 64..512, multiple of 32 */
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */

@@ -773,3 +773,8 @@ def test_region_mode_is_bit_identical(vrt, oracle, volk, dirk, live):
         got = t.trace_rays_cu(pos, d, [1.0, 1.0, 1.0], 0x20000000, 900, live_translucency=live)
         _assert_same(got, want[:4], "region log2=%d rounds=%d refill=%d" % (log2, rounds, refill))
     assert len(np.unique(want[2])) > 50
+    t.close()
+    tb = vrt.TraceRaysCu(ob, planes, trc, bricked=True)          # region mode over the 2x2x2-brick layout
+    tb.set_option(vrt.VRT_OPT_REGION_LOG2, 5)
+    _assert_same(tb.trace_rays_cu(pos, d, [1.0, 1.0, 1.0], 0x20000000, 900, live_translucency=live), want[:4], "region mode, bricked")
+    tb.close()

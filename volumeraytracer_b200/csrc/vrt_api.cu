@@ -778,7 +778,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
         const unsigned long long vb = s->paired ? 32ull : (s->dim + 1) * elem_size(s->store);
         p.row1 = (unsigned long long)p.bz * vb; p.row2 = (unsigned long long)(uint32_t)(p.by * p.bz) * vb; p.row3 = (unsigned long long)(uint32_t)((p.by + 1u) * p.bz) * vb;
     }
-    p.pair = s->paired ? 1 : 0;
+    p.pair = s->paired ? 1 : 0; p.brick = s->bricked ? 1 : 0;
     p.one[0] = p.one[1] = 1.0f;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
@@ -793,7 +793,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     const int block = (int)s->opt_block.load();
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
     if (kver == 3 && !path && p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f) kver = 9;   // unit invscale: two multiplies fewer per step, same bits
-    if (region_log2 > 0 && s->dim == 3 && !path && !s->bricked && !s->tex)
+    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex)
         return enqueue_march_regions(s, p, di16, live, st, region_log2);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
     if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)

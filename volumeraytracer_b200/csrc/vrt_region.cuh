@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(128, 5) march3_region_kernel(const RegionParam
             {
                 const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
                 if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
-                if (m.pair) load_corners_pair(q, m, cell);     // uniform branch
-                else        load_corners<VoxT>(q, m, cell);
+                if (m.pair)       load_corners_pair(q, m, cell);     // uniform branches
+                else if (m.brick) load_corners_brick<VoxT>(q, m.volume, px >> 16, py >> 16, pz >> 16, m.nby, m.nbz);
+                else              load_corners<VoxT>(q, m, cell);
             }
             if (LIVE)                                                                            // cu:337-341
             {

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -779,6 +780,15 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
         p.row1 = (unsigned long long)p.bz * vb; p.row2 = (unsigned long long)(uint32_t)(p.by * p.bz) * vb; p.row3 = (unsigned long long)(uint32_t)((p.by + 1u) * p.bz) * vb;
     }
     p.pair = s->paired ? 1 : 0; p.brick = s->bricked ? 1 : 0;
+    {
+        // |dir|^2 range of the fast loop (see div_is_fast_in): [max(2^-95, m^2 * 2^17 * 1.01), 2^97), m = max |invscale|; an unusable m
+        // (NaN, inf, huge) leaves an empty range and every step goes through the generic code
+        const float m = std::fmax(std::fabs(p.invx), std::fmax(std::fabs(p.invy), std::fabs(p.invz)));
+        float lo = m * m * 131072.0f * 1.01f;
+        uint32_t lo_bits = 0x70000000u;
+        if (lo == lo && lo < 0x1p97f) { if (lo < 0x1p-95f) lo = 0x1p-95f; memcpy(&lo_bits, &lo, 4); }
+        p.dot_lo = lo_bits; p.dot_span = 0x70000000u - lo_bits;
+    }
     p.one[0] = p.one[1] = 1.0f;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;

@@ -603,7 +603,8 @@ def test_channel3_edge_values_and_degenerate_directions(vrt, oracle):
     rows = rng.integers(0, n, 600)
     d[rows, rng.integers(0, 3, 600)] = special[rng.integers(0, len(special), 600)]
     d[rows[:60]] = 0.0
-    for isc, iters in (([1.0, 1.0, 1.0], 300), ([0.5, 2.0, 1.25], 77)):
+    for isc, iters in (([1.0, 1.0, 1.0], 300), ([0.5, 2.0, 1.25], 77), ([-1.0, 2.0, -0.5], 60), ([0.0, 0.0, 0.0], 9), ([1e20, 1.0, 1.0], 9),
+                       ([1e-20, 1.0, 3e4], 40), ([float('nan'), 1.0, 1.0], 5), ([float('inf'), 1.0, 1.0], 5)):
         want = oracle.trace(vol, shape, pos, d, isc, iters, round_mode=oracle.ROUND_DEVICE)
         t = vrt.TraceRaysCu.from_interleaved(shape, vol, tr)
         for kernel, refill, poll in ((0, 32, 128), (3, 1, 1), (3, 0, 7), (2, 32, 32), (1, 8, 500), (6, 32, 32)):

@@ -4,6 +4,8 @@
   (c) the reference's CPU build through the oracle's ROUND_HOST mode -- within the north_star tolerance
       (1e-3 voxel, 1e-5 rad on smooth fields).
 Run on the B200 box: pytest -m gpu."""
+import os
+
 import numpy as np
 import pytest
 
@@ -526,6 +528,16 @@ def test_dropin_splits_large_batches_across_devices(vrt, oracle):
     ob, _, planes, trc = oracle.prep(shape, ior, tr)
     p2, d2 = oracle.normalise(shape, ior, pos, d)
     want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 200, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])
+    # the dynamic piece queue (VRT_SPLIT_PIECES): 1.3 M rays = 3 pieces of >= 2^19 rays, also on a single device
+    pos, d = S.random_rays(shape, 1300000, seed=10)
+    os.environ["VRT_SPLIT_PIECES"] = "4"
+    try:
+        got = sc.trace(pos, d, [1, 1, 1], 0, 60)
+    finally:
+        del os.environ["VRT_SPLIT_PIECES"]
+    p2, d2 = oracle.normalise(shape, ior, pos, d)
+    want = oracle.trace(oracle.fold(planes, trc), ob, p2, d2, [1, 1, 1], 60, round_mode=oracle.ROUND_DEVICE)
     assert EQ(got[0], want[0] + np.uint32(0x10000)) and EQ(got[1], want[1]) and EQ(got[2], want[2])
 
 

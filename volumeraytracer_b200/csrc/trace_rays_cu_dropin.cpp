@@ -23,6 +23,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -129,14 +130,27 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
     if (const char *e = std::getenv("VRT_LIVE_TRANSLUCENCY")) if (std::atoi(e) != 0) flags |= VRT_TRACE_LIVE_TRANSLUCENCY;
 
     const size_t ndev = std::min<size_t>(st->scenes.size(), std::max<size_t>(1, (n + 0x7FFF) / 0x8000));   // cu:806
+    // The batch is cut into ndev * pieces contiguous pieces which the device threads take in order from a shared counter.
+    // pieces = 1 (default) is a static split, best when every ray runs about as long as its neighbours; VRT_SPLIT_PIECES=<k>
+    // hands out k pieces per device dynamically, like the reference's chunk queue (cu:820-821), for batches whose step counts
+    // vary systematically along the ray order (each piece is a full vrt_trace pipeline, so keep k small).
+    size_t pieces = 1;
+    if (const char *e = std::getenv("VRT_SPLIT_PIECES")) { const int k = std::atoi(e); if (k > 0 && k <= 64) pieces = (size_t)k; }
+    const size_t npieces = std::min<size_t>(ndev * pieces, std::max<size_t>(ndev, (n + 0x7FFFF) / 0x80000));   // at least 2^19 rays per dynamic piece
+    std::atomic<size_t> next{0};
     std::vector<std::string> errors(ndev);
+    const bool dynamic = npieces > ndev;
     auto work = [&](size_t k) {
-        const size_t lo = n * k / ndev, hi = n * (k + 1) / ndev;
-        if (hi == lo) return;
-        int rc = vrt_trace(st->scenes[k], hi - lo, start_position.data() + lo * dim, start_direction.data() + lo * dim, dtype_of<DirType>::value,
-                           scale_vec.data(), minimum_brightness, iterations, flags, end_position.data() + lo * dim, end_direction.data() + lo * dim,
-                           end_iteration.data() + lo, remaining_light.data() + lo, trace_paths ? path.data() + lo * dim * iterations : nullptr);
-        if (rc != VRT_OK) errors[k] = vrt_last_error();
+        // static split: device k traces piece k; dynamic: whatever piece is next
+        for (size_t piece = dynamic ? next.fetch_add(1) : k; piece < npieces; piece = dynamic ? next.fetch_add(1) : npieces)
+        {
+            const size_t lo = n * piece / npieces, hi = n * (piece + 1) / npieces;
+            if (hi == lo) continue;
+            int rc = vrt_trace(st->scenes[k], hi - lo, start_position.data() + lo * dim, start_direction.data() + lo * dim, dtype_of<DirType>::value,
+                               scale_vec.data(), minimum_brightness, iterations, flags, end_position.data() + lo * dim, end_direction.data() + lo * dim,
+                               end_iteration.data() + lo, remaining_light.data() + lo, trace_paths ? path.data() + lo * dim * iterations : nullptr);
+            if (rc != VRT_OK) { errors[k] = vrt_last_error(); return; }
+        }
     };
     if (ndev == 1) work(0);
     else

@@ -19,10 +19,22 @@
 // TU 1 of 2: includes the reference .cu (TraceRaysCu<> + trace_rays_cpu<>).  The scene-level wrappers
 // live in ref_harness_scene.cpp because tuple_io.h and io_util.h both declare `print`.
 
+#ifdef VRTREF_HEADER_ONLY   // libvrt_dropin.so: only the boundary class, declared by the reference's header and DEFINED by our shim
+#include <vector>
+#include <memory>
+#include <string>
+#include <stdexcept>
+#include <cstdint>
+#include <cstddef>
+#include <iostream>
+#include <omp.h>
+#include "cuda_volume_raytracer.h"
+#else
 #ifndef VRTREF_CUDA      // VRTREF_CUDA: the same harness compiled by nvcc for sm_100 = the reference's own CUDA trace
 #define NCUDA 1
 #endif
 #include "cuda_volume_raytracer.cu"   // found via -I$(REF_SRC)
+#endif
 
 #include <cstring>
 #include <string>
@@ -85,6 +97,7 @@ int tracer_trace(void *h, size_t n, const uint32_t *pos, const DirType *dir, con
     VRTREF_CATCH
 }
 
+#ifndef VRTREF_HEADER_ONLY
 // The LIVE-translucency instantiation of the reference marcher (cu:337-341,370-373): the template is
 // given a real translucency_t* and brightness_t instead of DummyArray/DummyObject.  Mirrors what
 // trace_rays_cu_impl does around the call (fill_struct cu:468-488, read_struct cu:490-516,
@@ -128,6 +141,7 @@ int trace_live_dim(DiffType *vol, const uint32_t *tr, const size_t *bounds, cons
     VRTREF_CATCH
 }
 
+#endif
 } // namespace
 
 extern "C" {
@@ -148,7 +162,7 @@ int vrtref_tracer_new_f32(void **out, const size_t *bounds, int dim, const float
 int vrtref_tracer_new_i16(void **out, const size_t *bounds, int dim, const int16_t *const *diff, const uint32_t *tr) { return tracer_new<diff_t>(out, bounds, dim, diff, tr); }
 void vrtref_tracer_delete_f32(void *h) { delete static_cast<TracerBox<float>*>(h); }
 void vrtref_tracer_delete_i16(void *h) { delete static_cast<TracerBox<diff_t>*>(h); }
-#ifndef VRTREF_CUDA   // private member access needs -fno-access-control (host build only)
+#if !defined(VRTREF_CUDA) && !defined(VRTREF_HEADER_ONLY)   // private member access needs -fno-access-control (host build only)
 void vrtref_tracer_interleaved_f32(void *h, float *out)   { auto *b = static_cast<TracerBox<float>*>(h);  size_t n = b->diff[0].size() * (b->diff.size() + 1); std::memcpy(out, b->tracer->_diff_interleaved.get(), n * sizeof(float)); }
 void vrtref_tracer_interleaved_i16(void *h, int16_t *out) { auto *b = static_cast<TracerBox<diff_t>*>(h); size_t n = b->diff[0].size() * (b->diff.size() + 1); std::memcpy(out, b->tracer->_diff_interleaved.get(), n * sizeof(int16_t)); }
 #endif
@@ -162,6 +176,7 @@ VRTREF_TRACER_TRACE(vrtref_tracer_trace_f32_i16, float, int16_t)
 VRTREF_TRACER_TRACE(vrtref_tracer_trace_i16_f32, diff_t, float)
 VRTREF_TRACER_TRACE(vrtref_tracer_trace_i16_i16, diff_t, int16_t)
 
+#ifndef VRTREF_HEADER_ONLY
 // ---- live translucency / minimum brightness: trace_rays_cpu on an interleaved volume ----
 #define VRTREF_TRACE_LIVE(NAME, DIFF, DIR)                                                                                        \
 int NAME(const DIFF *vol, const uint32_t *tr, const size_t *bounds, int dim, const float *invscale, size_t n, const uint32_t *pos, \
@@ -178,5 +193,7 @@ VRTREF_TRACE_LIVE(vrtref_trace_live_f32_f32, float, float)
 VRTREF_TRACE_LIVE(vrtref_trace_live_f32_i16, float, int16_t)
 VRTREF_TRACE_LIVE(vrtref_trace_live_i16_f32, diff_t, float)
 VRTREF_TRACE_LIVE(vrtref_trace_live_i16_i16, diff_t, int16_t)
+
+#endif
 
 } // extern "C"

@@ -205,6 +205,30 @@ def test_against_reference_cuda_kernel(vrt, oracle):
         rt.close()
 
 
+def test_reference_boundary_class_on_the_dropin(vrt, oracle):
+    """The reference's own class TraceRaysCu<float|diff_t> (cuda_volume_raytracer.h:61-115), constructed and called exactly as
+    image_util.cpp does, with its member functions DEFINED by the drop-in shim: all four volume x direction type combinations,
+    3-D and 2-D, with and without path output, equal the reference's CUDA build and the oracle bit for bit."""
+    from oracle import ref
+    if not ref.available("dropin"):
+        pytest.skip("oracle/_ref/libvrt_dropin.so not built")
+    for volk, dirk in (("f32", "f32"), ("i16", "i16"), ("f32", "i16"), ("i16", "f32")):
+        for shape in ((34, 30, 38), (60, 45)):
+            ob, planes, trc, vol, t = _mk(vrt, oracle, shape, 17, volk)
+            t.close()
+            pos, d = S.random_rays(ob, 40000, seed=23, dir_kind=dirk)           # > 32 768: more than one reference chunk
+            pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+            isc = [1.0] * len(shape)
+            rt = ref.RefTracer(ob, planes, trc, cuda="dropin")
+            got = rt.trace(pos, d, isc, 0, 300)
+            want = oracle.trace(vol, ob, pos, d, isc, 300, round_mode=oracle.ROUND_DEVICE)
+            _assert_same(got, want[:4], "TraceRaysCu<> on the drop-in %s/%s %s" % (volk, dirk, shape))
+            gotp = rt.trace(pos[:300], d[:300], isc, 0, 50, trace_path=True)
+            wantp = oracle.trace(vol, ob, pos[:300], d[:300], isc, 50, trace_path=True, round_mode=oracle.ROUND_DEVICE)
+            _assert_same(gotp, wantp, "TraceRaysCu<> on the drop-in, paths %s/%s %s" % (volk, dirk, shape))
+            rt.close()
+
+
 def test_within_tolerance_of_reference_cpu_on_smooth_field(vrt, oracle):
     """north_star tolerance vs the reference's CPU trace (ROUND_HOST = bit-exact restatement of it): end positions
     within 1e-3 voxel, directions within 1e-5 rad, identical termination step counts, on a smooth analytic field."""

@@ -98,6 +98,26 @@ def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
     sc.close()
 
 
+def cfg_c2h(size=256, nray=1024, iterations=4096):
+    """config 2 through the HOST call with pageable buffers, for several chunk sizes (VRT_OPT_CHUNK_RAYS; 0 = the library's choice)"""
+    ior = W.ior_luneburg_torch(size, dev, 100.0 * size / 256.0); tr = W.clear_translucency_torch((size,) * 3, dev)
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr); torch.cuda.synchronize()
+    pos, d = W.rays_parallel_x(nray, nray, 30.0 * size / 256.0, 225.0 * size / 256.0, x0=2.0)
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    p_h = tpos.cpu().numpy().view(np.uint32); d_h = tdir.cpu().numpy()
+    n = p_h.size // 3
+    epos = np.zeros_like(p_h); edir = np.zeros_like(d_h); eit = np.zeros(n, np.uint32); light = np.zeros(n, np.uint32)
+    for chunk in (0, 0, 65536, 131072, 262144, 524288, 1048576, 0):
+        sc.set_option(vrt.VRT_OPT_CHUNK_RAYS, chunk)
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter(); sc.trace_host_buffers(p_h, d_h, [1, 1, 1], 0, iterations, epos, edir, eit, light); best = min(best, time.perf_counter() - t0)
+        steps = int(eit.astype(np.int64).sum())
+        print(json.dumps(dict(cfg="c2_hostcall_pageable", chunk=chunk, sec=round(best, 5), grays=round(steps / best / 1e9, 2))), flush=True)
+    sc.close()
+
+
 def cfg_c5h(size=1024, nray=4096, iterations=2048):
     """config 5 through the HOST call with PAGEABLE buffers (numpy arrays, like the std::vectors of the reference API)"""
     ior = W.ior_c5_torch(size, dev); tr = W.clear_translucency_torch((size,) * 3, dev)
@@ -225,4 +245,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["l2", "c2", "c5", "c4", "c3"]
     print(torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     for w in which:
-        {"c5h": cfg_c5h, "c4h": cfg_c4h, "c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()
+        {"c2h": cfg_c2h, "c5h": cfg_c5h, "c4h": cfg_c4h, "c1": cfg_c1, "c5": cfg_c5, "c5i": cfg_c5i, "c4": cfg_c4, "c3": cfg_c3, "c2": cfg_c2, "l2": cfg_l2, "latency": cfg_latency}[w]()

@@ -949,7 +949,9 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
 
     // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
-    if (chunk == 0) chunk = n <= (1u << 19) ? n : std::max<uint64_t>(1u << 19, (n + 15) / 16);
+    // at least 2^17 rays per chunk (one wave of the persistent grid), at most 16 chunks: config 2 (1 M rays) through pageable buffers
+    // runs 8 chunks at 224 G ray-steps/s instead of 2 chunks at 190
+    if (chunk == 0) chunk = n <= (1u << 17) ? n : std::max<uint64_t>(1u << 17, (n + 15) / 16);
     if (region > 0 && s->opt_chunk.load() == 0) chunk = std::max<uint64_t>(chunk, std::min<uint64_t>(n, 4u << 20));   // regions want many rays per sort
     if (want_path)
     {

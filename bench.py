@@ -4,22 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (config 5 of BASELINE.json): 1024^3 index volume
-n = 1.2 + 0.05 sin(2 pi x/256) cos(2 pi y/256) cos(2 pi z/256) -> 1022^3 x float4 gradient volume (17.08 GB) built on
-the GPU by the scene-prep kernels; 4096^2 = 16 777 216 parallel +x rays per GPU, cap 2048 steps (every ray runs the
-cap, so one pass = 34.36 G ray-steps per GPU).  A "step" of this benchmark is one such pass.
+Workload (config 5 of BASELINE.json, SURVEY.md section 8d, AS NAMED): 1024^3 index volume
+n = 1.2 + 0.05 sin(2 pi x/256) cos(2 pi y/256) cos(2 pi z/256) -> 1022^3 x float4 gradient volume (17.08 GB per GPU) built on
+the GPU by the scene-prep kernels; ONE batch of 4096^2 = 16 777 216 parallel +x rays, cap 2048 steps (every ray runs the cap:
+one pass = 34.36 G ray-steps), ray-sharded over the N GPUs as contiguous chunks -- STRONG scaling.  A "step" is one such pass.
 
   value     whole-job G ray-steps/s with volume and ray buffers resident in HBM (vrt_trace_device), CUDA events on the
             launching stream, max over ranks.  ray-steps = sum of the end_iteration output (reference: cu:953-956).
-  e2e       the same pass through the reference-facing host call (vrt_trace: pinned HOST ray buffers in, HOST results
-            out, copies inside the timed region).
-  roofline  algorithmic gather bytes (128 B per ray-step: 8 corners x 4 channels x fp32, cu:140-143) / launch time,
-            against the measured HBM copy bandwidth of MEASURED_PEAKS.json; `roofline_l2` does the same against a
-            random 32-byte-sector gather bandwidth measured on this GPU over an L2-resident buffer.
+  e2e       the same pass through the reference-facing host call (vrt_trace): the batch lives in ONE set of PAGEABLE host arrays
+            shared by the ranks (volumeraytracer_b200.dist.SharedBatch), every rank traces its chunk in place, copies inside the
+            timed region, max over ranks.  e2e.pinned_value: the same with the chunk cudaHostRegister'ed.
+  roofline  the roof that binds this kernel: instruction issue.  Warp-instructions per pass are COUNTED IN THIS RUN (an
+            instrumented copy of the kernel counts how often each of its blocks is issued; block lengths come from the SASS of
+            the shipped binary, tools/sass_blocks.py) against SMs x 4 schedulers x the SM clock sampled in this run.
+            roofline_hbm: SURVEY 8(d)'s algorithmic gather bytes (128 B per ray-step) / launch time against the measured HBM copy
+            bandwidth of MEASURED_PEAKS.json; roofline_l2: the same against a random-sector gather bandwidth measured here.
   cpu_baseline  the UNMODIFIED reference CPU marcher (oracle/_ref, trace_rays_cpu cu:376-394, all host threads) on a
             1/16 strided subsample of the same rays against the same volume bits (downloaded from the GPU).
-Multi-GPU (weak scaling): the staged volume is built on rank 0 and replicated with one NCCL broadcast; rank 0 prepares
-the global N x 16M-ray batch and scatters contiguous chunks; each rank marches its chunk; no per-step collective.
+  other_configs / reference_cuda / e2e_reference_api   (N=1; tools/bench_extras.py) configs 2-4 at full size with parity, the
+            reference's own CUDA kernel timed beside ours, and the reference's unmodified RaytraceScene::trace_rays on the drop-in.
+Multi-GPU: the staged scene is built on rank 0 and replicated by the C++ library (vrt_comm_* / vrt_scene_broadcast: in-place
+ncclBroadcast over NVLink, nccl_broadcast_gbs); every rank generates and normalises its rows of the ray grid on its own GPU and
+marches them; no per-step collective.  weak_scaling: round 1's figure (a full 4096^2 batch per GPU) as an extra.
 
 --impl reference: the reference's own CPU implementation of the path (oracle/_ref) on the host cores, on a bounded
 sample of the same workload (a y/z window of the ray grid with the matching analytic sub-volume, built on the CPU).
@@ -175,13 +181,18 @@ def run_reference_arm(args, rank, world):
         dt = time.perf_counter() - t0
     steps = int(out[2].astype(np.int64).sum())
     value = steps * args.steps / dt / 1e9
-    sample = "%d x %d ray window (1/%d of one GPU's 4096^2 rays) through the matching %dx%dx%d analytic sub-volume, cap %d" % (
+    sample = "%d x %d ray window (1/%d of the 4096^2 rays) through the matching %dx%dx%d analytic sub-volume, cap %d" % (
         window, window, (RAY_SIDE // window) ** 2, ob[0], ob[1], ob[2], ITERATIONS)
+    cfg = workload_config(args.gpus)
+    # say what this arm really runs: a bounded sample of the workload, not the 17 GB volume / 16.8 M rays (a smaller volume is
+    # kinder to the CPU's caches, so the sample flatters the reference, not us)
+    cfg["workload"] = "config 5, BOUNDED SAMPLE for the CPU arm: " + sample + " (full workload: " + cfg["workload"] + ")"
+    cfg["rays_per_step"] = window * window
     line = {
         "impl": "reference", "metric": "ray-steps/sec", "value": value, "unit": "G ray-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "G ray-steps/s", "cores": threads, "kind": "reference" if use_ref else "port", "sample": sample},
         "e2e": {"value": value, "unit": "G ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "setup_s": round(time.time() - t_setup - dt, 1),
@@ -190,15 +201,74 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(n_gpus):
-    return {"workload": "config 5: 1024^3 index volume (1022^3 float4 gradient volume, 17.08 GB), 4096^2 parallel +x rays per GPU x cap 2048 steps",
-            "volume": "n=1.2+0.05 sin(2pi x/256) cos(2pi y/256) cos(2pi z/256)", "rays_per_gpu": RAY_SIDE * RAY_SIDE, "iterations": ITERATIONS,
+    return {"workload": "config 5: 1024^3 index volume (1022^3 float4 gradient volume, 17.08 GB per GPU), ONE batch of 4096^2 = 16 777 216 parallel +x rays "
+                        "x cap 2048 steps, ray-sharded over %d GPU(s) (strong scaling)" % n_gpus,
+            "volume": "n=1.2+0.05 sin(2pi x/256) cos(2pi y/256) cos(2pi z/256)", "rays_total": RAY_SIDE * RAY_SIDE,
+            "rays_per_gpu": RAY_SIDE * RAY_SIDE // n_gpus, "iterations": ITERATIONS,
             "scene": "float scene / float dirs, invscale 1, shipped translucency behaviour (compiled out, cu:785)",
-            "parallelism": "rays%d (contiguous ray chunks, volume replicated by one NCCL broadcast, no per-step collective)" % n_gpus,
-            "l2": "inputs larger than L2 (17 GB volume, 0.4 GB ray buffers); no explicit flush"}
+            "parallelism": "rays%d (contiguous ray chunks of one batch, results in place; volume replicated once by NCCL broadcast from the C++ library; "
+                           "no per-step collective)" % n_gpus,
+            "l2": "inputs larger than L2 (17 GB volume; ray buffers 0.4 GB / N); no explicit flush"}
 
 
 # ---------------------------------------------------------------------------------------------------
 # our arm
+
+def sass_block_lengths():
+    """SASS lengths of the marcher's blocks: the committed profiles/*_sass_blocks.json, checked against the shipped binary when the
+    CUDA binary tools are on the box (tools/sass_blocks.py is re-run and the opcode-stream hashes compared)."""
+    path = os.path.join(ROOT, "profiles", "r02_sass_blocks.json")
+    committed = None
+    try:
+        committed = json.load(open(path))
+    except Exception:
+        pass
+    live = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_blocks
+        live = sass_blocks.analyse(sass_blocks.disassemble(os.path.join(ROOT, "volumeraytracer_b200", "libvrt_b200.so"), sass_blocks.DEFAULT_KERNEL))
+    except BaseException:
+        live = None
+    if live is not None:
+        return live, ("read off the shipped libvrt_b200.so in this run (tools/sass_blocks.py)" +
+                      ("; equals committed profiles/r02_sass_blocks.json" if committed and committed.get("sass_sha1") == live["sass_sha1"]
+                       else "; committed profiles/r02_sass_blocks.json is STALE or missing"))
+    if committed is not None:
+        return committed, "committed profiles/r02_sass_blocks.json (cuobjdump/nvdisasm not available in this run)"
+    return None, "unavailable"
+
+
+def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
+    """The roof that binds the marcher on this workload: instruction issue.  Warp-instructions of one pass = (how often each block
+    of the kernel was issued, COUNTED IN THIS RUN by an instrumented copy of the kernel) x (the block's SASS length); peak = SMs x 4
+    schedulers x SM clock sampled in this run."""
+    import torch
+    blocks, src = sass_block_lengths()
+    if blocks is None:
+        return None
+    scene.set_option(vrt.VRT_OPT_KERNEL, 10)               # allocates / zeroes the counters
+    one_pass()
+    torch.cuda.synchronize()
+    cnt = [scene.get_option(vrt.VRT_INFO_STAT_BASE + k) for k in range(8)]
+    scene.set_option(vrt.VRT_OPT_KERNEL, 0)
+    names = ["outer", "refill", "fast_step", "reload", "mid", "generic", "retire"]
+    b = blocks["blocks"]
+    warp_instr = sum(cnt[i] * b[nm] for i, nm in enumerate(names))
+    num_sms = scene.get_option(vrt.VRT_INFO_NUM_SMS)
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    peak = num_sms * 4 * sm_mhz * 1e6
+    ach = warp_instr / launch_s
+    warp_steps = cnt[2]
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-instr/s", "frac": ach / peak,
+            "traffic": None, "warp_instructions_per_pass": warp_instr, "warp_steps_per_pass": warp_steps,
+            "warp_instructions_per_warp_step": warp_instr / max(warp_steps, 1),
+            "lane_efficiency": cnt[7] / max(32 * warp_steps, 1), "reloads_per_warp_step": cnt[3] / max(warp_steps, 1),
+            "block_issue_counts": dict(zip(names + ["lane_steps"], cnt)), "block_sass_lengths": b, "sass_lengths_source": src,
+            "num_sms": num_sms, "sm_mhz": sm_mhz, "launch_ms": launch_s * 1e3,
+            "how": "counts from one extra pass of the instrumented kernel copy (VRT_OPT_KERNEL 10, outside the timed region); "
+                   "time and clock from the timed region; cross-check against ncu smsp__inst_executed.sum in profiles/"}
+
 
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -209,59 +279,54 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)                # plumbing only: barriers, timing reductions, the unique-id exchange
+        host_group = dist.new_group(backend="gloo")                   # host-side barriers that keep the GPUs idle
+
+        def exchange(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = vrt.Comm(local_rank, rank, world, exchange)            # the product's own NCCL communicator (C++ library, dlopen'ed libnccl)
 
     size, side, iters = args.size, args.ray_side, args.iterations
-    n_local = side * side
+    n_total = side * side
     nvox = (size - 2) ** 3
 
-    # ---- scene: built once on rank 0 (GPU scene prep), replicated by ONE NCCL broadcast over NVLink --------------
+    # ---- scene: built once on rank 0 (GPU scene prep), replicated by the C++ library with in-place ncclBroadcasts over NVLink ----
     t0 = time.time()
     scene0 = None
+    ior = None
     if rank == 0:
         ior = W.ior_c5_torch(size, dev)
         tr = W.clear_translucency_torch((size,) * 3, dev)
         scene0 = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr)
         del tr
+    bcast = None
     if world > 1:
-        vol_t = torch.empty(nvox * 4, dtype=torch.float32, device=dev)
-        if rank == 0:
-            scene0.export_device(vol_t)
-        torch.cuda.synchronize()
-        tb = time.time()
-        vd.broadcast_volume(vol_t, src=0)                     # ONE collective, at scene creation (NCCL over NVLink)
-        torch.cuda.synchronize()
-        bcast_s = time.time() - tb
-        scene = vrt.TraceRaysCu.from_device([size - 2] * 3, vol_t, None, borrow=True)
+        torch.cuda.synchronize(); dist.barrier()
+        scene, bcast_s = comm.broadcast_scene(scene0, root=0)
+        payload = scene.storage_info()[2] + nvox * 4 + size ** 3 * 4          # staged volume + translucency plane + ior (kept for the normalise step)
+        t_all = torch.tensor([bcast_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        bcast = {"seconds": float(t_all.item()), "bytes": int(payload), "gb_per_s": payload / float(t_all.item()) / 1e9,
+                 "what": "vrt_scene_broadcast: in-place ncclBroadcast of the staged 17.08 GB volume + 4.27 GB translucency plane + 4.29 GB ior on a "
+                         "communicator warmed by vrt_comm_create; device time (CUDA events), max over ranks"}
     else:
-        scene, bcast_s = scene0, 0.0
+        scene = scene0
 
-    # ---- rays: rank 0 prepares the global batch (world x side^2 rays over [2, size-3]^2) and scatters contiguous chunks
-    pos_t = torch.empty(n_local * 3, dtype=torch.int32, device=dev)
-    dir_t = torch.empty(n_local * 3, dtype=torch.float32, device=dev)
-    if rank == 0:
-        chunks_p, chunks_d = [], []
-        lo, hi = 2.0, size - 3.0
-        rows = world * side
-        for r in range(world):
-            y0 = lo + (hi - lo) * (r * side) / (rows - 1)
-            y1 = lo + (hi - lo) * (r * side + side - 1) / (rows - 1)
-            p, d = W.rays_parallel_x(side, side, y0, y1, x0=2.0, lo_z=lo, hi_z=hi)
-            tp = torch.from_numpy(p.view(np.int32).reshape(-1)).to(dev)
-            td = torch.from_numpy(d.reshape(-1)).to(dev)
-            scene0.normalise_rays_device(tp, td)                  # f2 on the GPU (needs ior, which only rank 0 keeps)
-            chunks_p.append(tp); chunks_d.append(td)
-        if world > 1:
-            dist.scatter(pos_t, chunks_p, src=0); dist.scatter(dir_t, chunks_d, src=0)
-        else:
-            pos_t, dir_t = chunks_p[0], chunks_d[0]
-        del chunks_p, chunks_d
-    else:
-        dist.scatter(pos_t, None, src=0); dist.scatter(dir_t, None, src=0)
-    if world > 1 and rank == 0:
-        ior = None
+    # ---- rays: ONE batch of side^2 rays; rank r owns rows [r*side/world, (r+1)*side/world) = a contiguous index range ----------------
+    j0, j1 = vd.chunk_bounds(side, world, rank)
+    lo, hi = 2.0, size - 3.0
+    p, d = W.rays_parallel_x(side, side, lo, hi, x0=2.0, rows=(j0, j1))
+    n_local = p.shape[0]
+    pos_t = torch.from_numpy(p.view(np.int32).reshape(-1)).to(dev)
+    dir_t = torch.from_numpy(d.reshape(-1)).to(dev)
+    scene.normalise_rays_device(pos_t, dir_t)                             # f2 on every rank's own GPU (ior travelled with the scene)
+    del p, d
     torch.cuda.synchronize()
     setup_s = time.time() - t0
 
@@ -277,6 +342,18 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
 
     for _ in range(args.warmup):
         one_pass()
@@ -298,34 +375,81 @@ def run_ours(args, rank, local_rank, world):
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     steps_local = int(eit.to(torch.int64).sum().item())
-
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    s_all = torch.tensor([steps_local], dtype=torch.int64, device=dev)
-    l_all = torch.tensor([launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(s_all, op=dist.ReduceOp.SUM); dist.all_reduce(l_all, op=dist.ReduceOp.SUM)
-    max_ms = float(t_ms.item()); steps_global = int(s_all.item())
+    max_ms = reduce_max(total_ms); steps_global = reduce_sum(steps_local); launches_global = reduce_sum(launches)
     value = steps_global * args.steps / (max_ms * 1e-3) / 1e9
 
-    # ---- e2e: the reference-facing host call, pinned host buffers, copies inside the timed region -------------------
+    # ---- e2e: ONE caller-owned batch in host memory shared by the ranks; every rank traces its chunk of it IN PLACE through the
+    # reference-facing host call (vrt_trace), PAGEABLE memory as a std::vector caller would hand over; copies inside the timed region
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_pos = torch.empty(n_local * 3, dtype=torch.int32).pin_memory(); h_dir = torch.empty(n_local * 3, dtype=torch.float32).pin_memory()
-    h_pos.copy_(pos_t.cpu()); h_dir.copy_(dir_t.cpu())
-    h_epos = torch.empty_like(h_pos).pin_memory(); h_edir = torch.empty_like(h_dir).pin_memory()
-    h_eit = torch.empty(n_local, dtype=torch.int32).pin_memory(); h_light = torch.empty(n_local, dtype=torch.int32).pin_memory()
-    scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)      # warm-up
+    tag = "vrt_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if world > 1 else os.getpid())
+    batch = vd.SharedBatch(tag, n_total, 3, np.float32, create=True) if rank == 0 else None
+    barrier()
+    if rank != 0:
+        batch = vd.SharedBatch(tag, n_total, 3, np.float32, create=False)
+    h_pos, h_dir, h_epos, h_edir, h_eit, h_light = batch.slices(world, rank)
+    assert h_eit.shape[0] == n_local, (h_eit.shape, n_local)
+    h_pos[:] = pos_t.cpu().numpy().view(np.uint32); h_dir[:] = dir_t.cpu().numpy()
+    scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)      # warm-up (also faults the output pages in)
     barrier()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
         scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)
     e2e_s = time.perf_counter() - t1
     barrier()
-    e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-    e2e_value = steps_global * e2e_steps / float(e_t.item()) / 1e9
-    e2e_ok = bool(torch.equal(h_eit, eit.cpu()) and torch.equal(h_epos, epos.cpu()))
+    e2e_value = steps_global * e2e_steps / reduce_max(e2e_s) / 1e9
+    e2e_ok = bool(np.array_equal(h_eit, eit.cpu().numpy().view(np.uint32)) and np.array_equal(h_epos, epos.cpu().numpy().view(np.uint32)))
+    e2e_ok_all = reduce_sum(0 if e2e_ok else 1) == 0
+    whole_batch_steps = int(batch.arrays["eit"].astype(np.int64).sum()) if rank == 0 else 0      # rank 0 reads ALL ranks' results out of the one batch
+    # the same with the chunk of the batch registered as pinned memory (what a caller that owns its allocation can do)
+    e2e_pinned = None
+    try:
+        cudart = torch.cuda.cudart()
+        regs = []
+        for a in (h_pos, h_dir, h_epos, h_edir, h_eit, h_light):
+            rc = cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister %s" % rc)
+            regs.append(a)
+        scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)
+        dtp = time.perf_counter() - t1
+        barrier()
+        e2e_pinned = steps_global * e2e_steps / reduce_max(dtp) / 1e9
+        for a in regs:
+            cudart.cudaHostUnregister(a.ctypes.data)
+    except Exception:
+        e2e_pinned = None
+        barrier(); barrier()
+    del h_pos, h_dir, h_epos, h_edir, h_eit, h_light
+    batch.close()
 
+    # ---- weak-scaling figure (round 1's headline), as an extra: every rank marches a full 4096^2 batch of its own --------------------
+    weak = None
+    if world > 1 and args.weak_steps > 0:
+        pw, dw = W.rays_parallel_x(side, side, lo, hi, x0=2.0)
+        wp = torch.from_numpy(pw.view(np.int32).reshape(-1)).to(dev); wd = torch.from_numpy(dw.reshape(-1)).to(dev)
+        scene.normalise_rays_device(wp, wd)
+        we = torch.empty_like(wp); wdd = torch.empty_like(wd)
+        wi = torch.empty(n_total, dtype=torch.int32, device=dev); wl = torch.empty(n_total, dtype=torch.int32, device=dev)
+        scene.trace_device(wp, wd, isc, 0, iters, epos=we, edir=wdd, eit=wi, light=wl, stream=stream)
+        barrier()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.weak_steps):
+            scene.trace_device(wp, wd, isc, 0, iters, epos=we, edir=wdd, eit=wi, light=wl, stream=stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        w_ms = reduce_max(a.elapsed_time(b))
+        w_steps = reduce_sum(int(wi.to(torch.int64).sum().item()))
+        weak = {"value": w_steps * args.weak_steps / (w_ms * 1e-3) / 1e9, "unit": "G ray-steps/s", "rays_per_gpu": n_total, "steps": args.weak_steps,
+                "ms_per_step": w_ms / args.weak_steps, "scaling": "weak"}
+        del wp, wd, we, wdd, wi, wl, pw, dw
+
+    line = None
     if rank == 0:
         peaks, peak_src = measured_peaks()
         launch_s = float(np.mean(per_launch_ms)) * 1e-3
@@ -337,23 +461,14 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_ray_step": B_ALG_F32, "ray_steps_per_launch": steps_local,
-                "launch_ms": launch_s * 1e3,
-                "note": "coherent bundle: the 8-corner gathers are served from registers/L1 (cell cache), so the algorithmic gather "
-                        "rate exceeds DRAM bandwidth; see roofline_l2 and profiles/ for the counters"}
-        # what actually bounds the kernel on this coherent workload is instruction issue: report that
-        # utilisation too, from the committed ncu instruction count per warp-step and the clock sampled in this run
-        roof_issue = None
-        try:
-            wi = json.load(open(prof)).get("warp_instructions_per_warp_step")
-            sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-            peak_issue = 148 * 4 * sm_hz * 1e6                      # one warp-instruction per scheduler per clock, 4 schedulers per SM
-            ach_issue = wi * (steps_local / 32.0) / launch_s
-            roof_issue = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s", "frac": ach_issue / peak_issue,
-                          "warp_instructions_per_warp_step": wi, "source": "profiles/ncu_c5_summary.json (ncu smsp__inst_executed.sum)"}
-        except Exception:
-            roof_issue = None
+        roof_hbm = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": traffic, "traffic_note": "ncu dram bytes of one 16.8 M-ray launch (profiles/ncu_c5_summary.json)", "peak_source": peak_src,
+                    "bytes_per_ray_step": B_ALG_F32, "ray_steps_per_launch": steps_local, "launch_ms": launch_s * 1e3,
+                    "note": "SURVEY 8(d) algorithmic gather bytes / launch time.  Not a binding roof on this coherent workload: the 8-corner gathers "
+                            "are served from the register cell cache and L1, so the algorithmic rate exceeds DRAM bandwidth (see `roofline`)"}
+        roof = issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt)
+        if roof is not None:
+            roof["traffic"] = traffic
         g = C.c_double(0.0)
         roof_l2 = None
         if vrt.lib().vrt_measure_gather_bandwidth(local_rank, 32 << 20, 32, 3, C.byref(g)) == 0 and g.value > 0:
@@ -361,26 +476,65 @@ def run_ours(args, rank, local_rank, world):
                        "how": "random 32-byte-sector gather over a 32 MiB (L2-resident) buffer, measured in this run"}
         line = {
             "metric": "ray-steps/sec", "value": value, "unit": "G ray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "G ray-steps/s", "h2d_bytes_per_step": n_local * 24 * world, "d2h_bytes_per_step": n_local * 32 * world,
-                    "steps": e2e_steps, "matches_device_run": e2e_ok, "call": "vrt_trace (C ABI, pinned host buffers)"},
-            "gpu_launches": int(l_all.item()), "roofline": roof, "roofline_l2": roof_l2, "roofline_issue": roof_issue,
-            "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast_s": round(bcast_s, 3),
+            "e2e": {"value": e2e_value, "unit": "G ray-steps/s", "h2d_bytes_per_step": n_total * 24, "d2h_bytes_per_step": n_total * 32,
+                    "steps": e2e_steps, "matches_device_run": e2e_ok_all, "whole_batch_ray_steps_read_by_rank0": whole_batch_steps,
+                    "call": "vrt_trace (C ABI) on each rank's contiguous chunk of ONE batch held in PAGEABLE host memory shared by the ranks; results in place",
+                    "pinned_value": e2e_pinned, "pinned_note": "same call with the chunk cudaHostRegister'ed (registration outside the timed region)"},
+            "gpu_launches": launches_global, "roofline": roof if roof is not None else roof_hbm, "roofline_hbm": roof_hbm, "roofline_l2": roof_l2,
+            "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast": bcast,
+            "nccl_broadcast_gbs": bcast["gb_per_s"] if bcast else None, "weak_scaling": weak,
             "kernel": {"variant": scene.get_option(vrt.VRT_OPT_KERNEL), "block": scene.get_option(vrt.VRT_OPT_BLOCK_THREADS),
                        "refill": scene.get_option(vrt.VRT_OPT_REFILL), "steps_per_poll": scene.get_option(vrt.VRT_OPT_STEPS_PER_POLL)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line.update(cpu_baseline_and_parity(scene, pos_t, dir_t, epos, edir, eit, side, iters))
+            line.update(cpu_baseline_and_parity(scene, ior, pos_t, dir_t, epos, edir, eit, side, iters, size))
+    del ior
+    # ---- extra legs ---------------------------------------------------------------
+    extras = [] if args.extras == "none" else (["other", "refcuda", "refapi"] if args.extras == "all" else args.extras.split(","))
+    if world == 1 and extras:
+        del pos_t, dir_t, epos, edir, eit, light
+        scene.close()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extras as X
+        with quiet_stdout():
+            if "other" in extras:
+                line["other_configs"] = X.other_configs(dev)
+            if "refcuda" in extras:
+                line["reference_cuda"] = X.reference_cuda(dev)
+            if "refapi" in extras:
+                line["e2e_reference_api"] = X.e2e_reference_api(dev)
+    elif world > 1 and "refapi" in extras:
+        # ONE process driving all N GPUs through the reference's own API (the reference's multi-GPU model, cu:804-843): rank 0 runs
+        # it after the ranks have released their GPUs; the others wait on a host-side (gloo) barrier
+        del pos_t, dir_t, epos, edir, eit, light
+        scene.close()
+        if comm is not None:
+            comm.close(); comm = None
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_extras as X
+            with quiet_stdout():
+                line["e2e_reference_api"] = X.e2e_reference_api(dev, names=("c3",), n_devices=world)
+        dist.barrier(group=host_group)
+    if rank == 0:
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline_and_parity(scene, pos_t, dir_t, epos, edir, eit, side, iters):
+def cpu_baseline_and_parity(scene, ior, pos_t, dir_t, epos, edir, eit, side, iters, size):
     """Rank 0, N=1: (a) the reference CPU marcher timed on a strided 1/16 subsample against the same volume bits,
-    (b) bit-exact parity of the GPU result against the CPU oracle (device rounding) on a 1/256 subsample."""
+    (b) bit-exact parity of the GPU result against the CPU oracle (device rounding) on a 1/256 subsample,
+    (c) how many values of the GPU scene prep differ from the CPU prep (device log vs glibc log), on three 64-slice slabs."""
     from oracle import ref, oracle as orc
     out = {}
     vol, _ = scene.download_volume()
@@ -418,6 +572,37 @@ def cpu_baseline_and_parity(scene, pos_t, dir_t, epos, edir, eit, side, iters):
     ang = float(np.arccos(np.clip(np.sum(a * b, 1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1)), -1, 1)).max())
     out["parity"].update({"vs_reference_cpu_rounding": {"max_pos_err_voxel": dp, "max_dir_err_rad": ang,
                                                          "step_count_mismatches": int(np.sum(g_it != host[2]))}})
+    # ... and the same subsample with VRT_TRACE_ROUND_HOST: bit-exact against the reference's CPU rounding
+    try:
+        import torch
+        dev = pos_t.device
+        tp = torch.from_numpy(p_s.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d_s.reshape(-1)).to(dev)
+        gh = [o.cpu().numpy() for o in scene.trace_device(tp, td, [1, 1, 1], 0, iters, round_host=True)]
+        out["parity"]["round_host_bit_exact_vs_reference_cpu_rounding"] = bool(
+            np.array_equal(gh[0].view(np.uint32).reshape(-1, 3), host[0]) and np.array_equal(gh[1].reshape(-1, 3), host[1]) and np.array_equal(gh[2].view(np.uint32), host[2]))
+    except Exception as e:
+        out["parity"]["round_host_bit_exact_vs_reference_cpu_rounding"] = "error: %s" % e
+    # (c) GPU scene prep against the CPU prep (oracle.prep = the reference's ctor arithmetic with glibc logf), three slabs of 64 x-slices
+    try:
+        n_out = size - 2
+        v4 = vol.reshape(n_out, n_out * n_out * 4)
+        differing = compared = 0
+        worst = 0.0
+        for a0 in (0, (n_out - 64) // 2, n_out - 64):
+            slab = ior[a0:a0 + 66].cpu().numpy()
+            trs = np.full(slab.shape, 0xFFFFFFFF, np.uint32)
+            _, _, planes, trc = orc.prep(slab.shape, slab, trs)
+            ref_v = orc.fold(planes, trc).reshape(64, -1)
+            got_v = v4[a0:a0 + 64]
+            ne = ref_v != got_v
+            differing += int(ne.sum()); compared += int(ne.size)
+            if ne.any():
+                worst = max(worst, float(np.abs(ref_v[ne].astype(np.float64) - got_v[ne].astype(np.float64)).max()))
+        out["scene_prep_vs_cpu"] = {"values_compared": compared, "values_differing": differing, "max_abs_difference": worst,
+                                    "slabs": "x-slices [0,64), [479,543), [958,1022) of the 1022^3 x 4 gradient volume (18.8 % of it)",
+                                    "why": "device logf vs glibc logf differ in the last ulp for a few inputs; everything downstream of log is integer-exact"}
+    except Exception as e:
+        out["scene_prep_vs_cpu"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
 
 
@@ -433,6 +618,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-window", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weak-steps", type=int, default=3, help="N>1: timed passes of the weak-scaling extra (0 = skip)")
+    ap.add_argument("--extras", default="all", help="all | none | comma list of other,refcuda,refapi (extra legs; N>1 runs refapi only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -51,7 +51,13 @@ enum {
      * flag remaining_light is 0xFFFFFFFF for every ray and min_brightness is ignored, exactly as shipped (cu:785). */
     VRT_TRACE_LIVE_TRANSLUCENCY = 1u << 0,
     /* write the per-step polyline (ref trace_paths; cu:333,348,352-358): path[ray][iterations][dim], REVERSE order */
-    VRT_TRACE_PATHS             = 1u << 1
+    VRT_TRACE_PATHS             = 1u << 1,
+    /* round like the reference's CPU build: pos += static_cast<int32_t>(std::round(step)) (tuple_math.h:270-278: ties away from
+     * zero; NaN / out of range -> INT32_MIN) for the position update (cu:347) and the int16 direction narrowing (cu:359-363), and
+     * the CPU build's FMA contraction of the 2-D lerps.  Default: the reference's CUDA build (cvt.rni, ties to even, saturating).
+     * With this flag results are bit-identical to the reference's shipped Python module / CI, which link the CPU object
+     * (ref Makefile:78-79).  Single-launch marcher only (region mode and the layout variants are not used). */
+    VRT_TRACE_ROUND_HOST        = 1u << 2
 };
 
 /* vrt_scene_create* flags */
@@ -66,11 +72,12 @@ enum {
      * converts int16 to float before its first multiply anyway (cu:164), so results are bit-identical while the conversions
      * leave the hot loop (+37 % on coherent bundles, at twice the device memory).  This flag keeps the 8-byte voxels. */
     VRT_SCENE_KEEP_I16 = 1u << 2,
-    /* layout study: additionally stage the (float) volume in a CUDA 3-D array (block-linear tiling) and fetch the corners
+    /* LAYOUT STUDY ONLY (library built with -DVRT_STUDY, `make -C volumeraytracer_b200/csrc study`; the shipped library answers
+     * VRT_ERR_UNSUPPORTED): additionally stage the (float) volume in a CUDA 3-D array (block-linear tiling) and fetch the corners
      * through a point-sampled float4 texture object; filtering stays in software (hardware trilinear has 8-bit weights, the
      * reference uses 16).  3-D only, no path output; results bit-identical.  Not with VRT_SCENE_BORROW / _KEEP_I16 / _BRICK. */
     VRT_SCENE_LAYOUT_TEXTURE = 1u << 3,
-    /* layout study: store, for every cell, the voxel and its z neighbour side by side (32 bytes per cell, float scenes, 3-D):
+    /* LAYOUT STUDY ONLY (-DVRT_STUDY, see above): store, for every cell, the voxel and its z neighbour side by side (32 bytes per cell, float scenes, 3-D):
      * the two z-adjacent corners of a row become one aligned 256-bit load, a cell change 4 loads / 4 sectors instead of 8
      * loads / ~6 sectors, at twice the device memory.  Results bit-identical; works with path output, live translucency and
      * region mode.  Not with VRT_SCENE_BORROW / _KEEP_I16 / _BRICK / _TEXTURE. */
@@ -79,11 +86,13 @@ enum {
 
 /* vrt_scene_set_option keys (tuning; defaults are what bench.py measures) */
 enum {
-    VRT_OPT_KERNEL        = 0,  /* 0 default (= 3), 1 reference-like (reload every step), 2 register cell cache, 3 cell cache + packed
-                                   f32x2 + fast loop for cells without a possibly opaque corner (with invscale == (1,1,1) its
-                                   unit-invscale variant is launched: same bits, fewer instructions), 6 = 3 + empty-space fast path
-                                   (opt-in: coherent bundles through mostly empty volumes) */
-    VRT_OPT_BLOCK_THREADS = 1,  /* 64..512, multiple of 32 */
+    VRT_OPT_KERNEL        = 0,  /* settable: 0 default (= 3), 1 reference-like (reload every step), 2 register cell cache, 3 cell cache +
+                                   packed f32x2 + fast loop for cells without a possibly opaque corner, 6 = 3 + empty-space fast path
+                                   (opt-in: coherent bundles through mostly empty volumes).  Chosen implicitly, not settable: 9 = 3
+                                   specialised for invscale == (1,1,1) (same bits, fewer instructions; what 0/3 resolve to in that
+                                   case), 4 = brick layout (VRT_SCENE_LAYOUT_BRICK), 8 = host rounding (VRT_TRACE_ROUND_HOST), 2 for
+                                   path output; 5 / 7 = texture / z-pair layouts (study build only) */
+    VRT_OPT_BLOCK_THREADS = 1,  /* 32..256, multiple of 32 (the marcher is compiled with __launch_bounds__(256, 4)) */
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
     VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
@@ -95,6 +104,12 @@ enum {
     VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 12) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
+    VRT_INFO_NUM_SMS      = 101, /* read-only: multiprocessor count of the scene's device (cudaGetDeviceProperties) */
+    /* read-only, VRT_OPT_KERNEL 10 only (an instrumented copy of the default float / unit-invscale kernel, for measurement: same
+       results, slower): VRT_INFO_STAT_BASE + k, k = 0..7 = how many times block k of the marcher was ISSUED (per warp pass) since
+       the option was set: 0 outer loop, 1 refill, 2 fast-loop step, 3 cell reload, 4 fast-loop exit checks, 5 generic step,
+       6 retire/store, 7 lane-steps (per-thread, not per warp).  bench.py turns these into the issue-slot roofline. */
+    VRT_INFO_STAT_BASE    = 200,
     VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an
                                    incoherent batch's working set inside L1/L2 */
 };
@@ -130,10 +145,41 @@ VRT_API int vrt_scene_create_from_ior(vrt_scene **out, int device, int dim, cons
 /* ref: TraceRaysCu<DiffType>::~TraceRaysCu cu:974-989. */
 VRT_API int vrt_scene_destroy(vrt_scene *scene);
 
-/* Introspection: ref public member TraceRaysCu::_output_sizes (cuda_volume_raytracer.h:73) and the device buffers
- * (so that a multi-GPU caller can broadcast into them).  Any out pointer may be NULL. */
+/* Introspection: ref public member TraceRaysCu::_output_sizes (cuda_volume_raytracer.h:73).  Any out pointer may be NULL.
+ * *d_volume_interleaved is the device buffer ONLY when it holds the reference's layout in the API element type
+ * (volume_bytes = nvox*(dim+1)*sizeof(diff_dtype)); it is NULL when the staged copy differs (an int16 scene widened to
+ * float, the brick / study layouts) -- use vrt_scene_storage_info for what is really stored, vrt_scene_export_device /
+ * vrt_scene_download for a copy in the reference's layout, and vrt_scene_replicate / vrt_scene_broadcast to copy a scene
+ * to other GPUs. */
 VRT_API int vrt_scene_info(const vrt_scene *scene, int *device, int *dim, uint64_t *bounds, int *diff_dtype,
                            void **d_volume_interleaved, uint32_t **d_translucency, uint64_t *volume_bytes);
+/* What the device copy really is: element type of the staged volume, the VRT_SCENE_LAYOUT_* / _KEEP_I16 flags in effect,
+ * its size in bytes and its address. */
+VRT_API int vrt_scene_storage_info(const vrt_scene *scene, int *storage_dtype, unsigned *layout_flags, uint64_t *storage_bytes,
+                                   void **d_storage);
+
+/* Multi-GPU replication of a staged scene, the B200 replacement for the reference's per-device host upload loop
+ * (cu:676-686: one interleave + pageable cudaMemcpy of the whole volume per device).
+ *
+ * vrt_scene_replicate: ONE process driving several GPUs (the reference's own model, cu:804-843).  The staged buffers of `src`
+ * (volume as stored, translucency plane, ior if kept) are copied device-to-device over NVLink peer copies to devices[0..n-1]
+ * as a PIPELINED CHAIN src -> devices[0] -> devices[1] ... in 64 MiB slices, so every GPU receives and forwards at link speed
+ * and the whole replication takes about one volume's transfer time whatever n is.  out[i] receives the new scene on
+ * devices[i] (options copied from src).  *seconds (may be NULL) = wall time of the copies. */
+VRT_API int vrt_scene_replicate(const vrt_scene *src, int n, const int *devices, vrt_scene **out, double *seconds);
+
+/* One process per GPU (torchrun, MPI): NCCL.  libnccl.so.2 is loaded with dlopen on first use (the library has no link-time
+ * NCCL dependency; without NCCL these calls return VRT_ERR_UNSUPPORTED).  vrt_comm_unique_id fills 128 bytes on one rank; the
+ * caller hands them to every rank by whatever means it has (a file, MPI, torch.distributed) and each rank calls
+ * vrt_comm_create, which also runs a 4-byte broadcast so that NCCL's lazy connection set-up is not billed to the first scene.
+ * vrt_scene_broadcast replicates root's scene: on root `src` is the scene and *out == src; elsewhere src is ignored and *out
+ * is a new scene on the communicator's device.  The staged buffers are broadcast in place (no export copy).  *seconds (may be
+ * NULL) = device time of the payload broadcasts (CUDA events on the communicator's stream). */
+typedef struct vrt_comm vrt_comm;
+VRT_API int vrt_comm_unique_id(void *id_128_bytes);
+VRT_API int vrt_comm_create(vrt_comm **out, int device, int rank, int world, const void *id_128_bytes);
+VRT_API int vrt_comm_destroy(vrt_comm *comm);
+VRT_API int vrt_scene_broadcast(vrt_comm *comm, int root, vrt_scene *src, vrt_scene **out, double *seconds);
 /* Copy the staged volume back to the host (the reference keeps such a host copy itself: _diff_interleaved,
  * cuda_volume_raytracer.h:67).  host_volume: volume_bytes; host_translucency: nvox uint32; either may be NULL. */
 VRT_API int vrt_scene_download(const vrt_scene *scene, void *host_volume, uint32_t *host_translucency);
@@ -153,6 +199,11 @@ VRT_API int vrt_scene_get_option(const vrt_scene *scene, int key, int64_t *value
 VRT_API int vrt_trace(vrt_scene *scene, uint64_t n_rays, const uint32_t *start_pos, const void *start_dir, int dir_dtype,
                       const float *invscale, uint32_t min_brightness, uint32_t iterations, unsigned flags,
                       uint32_t *end_pos, void *end_dir, uint32_t *end_iter, uint32_t *remaining_light, uint32_t *path);
+
+/* ref: the "Warning, maximum iterations hitted" scan over end_iteration (cu:507-515).  1 if any ray of the calling thread's last
+ * vrt_trace ended at the iteration cap (end_iter == iterations), 0 if none did, -1 if unknown (no call yet / the call failed).
+ * The marcher sets a flag when it retires such a ray, so callers need not scan millions of results on one host thread. */
+VRT_API int vrt_trace_cap_hit(void);
 
 /* Same with DEVICE buffers on the scene's device, enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream);
  * returns without synchronising.  This is the call bench.py times for the HBM-resident figure. */

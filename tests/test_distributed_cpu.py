@@ -71,3 +71,58 @@ def test_chunk_bounds_cover_everything():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _shared_worker(rank, world, port, n_rays, tag, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from tests import scenes as S
+    from volumeraytracer_b200 import dist as vd
+    shape = (22, 20, 24)
+    ob = [s - 2 for s in shape]
+    ior, tr = S.random_scene(shape, seed=7, kind="f32")          # every rank can build the tiny scene itself; what is tested is the batch
+    _, _, planes, trc = orc.prep(shape, ior, tr)
+    vol = orc.fold(planes, trc)
+    batch = vd.SharedBatch(tag, n_rays, 3, np.float32, create=(rank == 0)) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        batch = vd.SharedBatch(tag, n_rays, 3, np.float32, create=False)
+    pos, d = S.random_rays(ob, n_rays, seed=3)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x4000)
+    if rank == 0:                                                 # ONE caller-owned batch
+        batch.arrays["pos"][:] = pos.reshape(-1); batch.arrays["dir"][:] = d.reshape(-1)
+    dist.barrier()
+    p_s, d_s, ep, ed, ei, li = batch.slices(world, rank)          # this rank's chunk, in place
+    res = orc.trace(vol, ob, np.asarray(p_s), np.asarray(d_s), [1, 1, 1], 200)
+    ep[:] = res[0].reshape(-1); ed[:] = res[1].reshape(-1); ei[:] = res[2]; li[:] = res[3]
+    dist.barrier()
+    if rank == 0:
+        want = orc.trace(vol, ob, pos, d, [1, 1, 1], 200)
+        a = batch.arrays
+        ok = (np.array_equal(a["epos"].reshape(-1, 3), want[0]) and np.array_equal(a["edir"].reshape(-1, 3), want[1])
+              and np.array_equal(a["eit"], want[2]) and np.array_equal(a["light"], want[3]))
+        open(out_path, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    batch.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rays", [1001, 3])
+def test_one_shared_batch_sharded_in_place_gloo(tmp_path, n_rays):
+    """Strong-scaling plumbing of bench.py: ONE batch in shared host arrays, each rank traces its contiguous chunk in place."""
+    out = str(tmp_path / "result.txt")
+    tag = "vrt_test_%d_%d" % (os.getpid(), n_rays)
+    mp.spawn(_shared_worker, args=(2, _free_port(), n_rays, tag, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(tag)]
+
+
+def test_ray_grid_rows_are_a_contiguous_slice():
+    sys.path.insert(0, ROOT)
+    from volumeraytracer_b200 import workloads as W
+    full_p, full_d = W.rays_parallel_x(37, 29, 2.0, 60.0, x0=2.0)
+    for j0, j1 in ((0, 10), (10, 37), (36, 37)):
+        p, d = W.rays_parallel_x(37, 29, 2.0, 60.0, x0=2.0, rows=(j0, j1))
+        assert np.array_equal(p, full_p[j0 * 29:j1 * 29]) and np.array_equal(d, full_d[j0 * 29:j1 * 29])

@@ -1,0 +1,280 @@
+"""Extra measurement legs of bench.py (imported by it; runnable alone: python tools/bench_extras.py [other|refcuda|refapi] ...).
+
+  other_configs      BASELINE.json configs 2, 3, 4 at FULL size on one GPU: device-resident rate, rate through the host call
+                     (pageable buffers), bit-exactness against the CPU oracle on a subsample (device rounding), the distance to
+                     the reference's CPU rounding, and bit-exactness of the VRT_TRACE_ROUND_HOST mode against the oracle's HOST
+                     mode (= the reference's CPU build, pinned bit for bit in tests/test_oracle_vs_reference.py).
+  reference_cuda     the reference's OWN CUDA kernel (cuda_volume_raytracer.cu:397-414, unmodified source compiled for sm_100 into
+                     oracle/_ref/libvrt_ref_cuda.so) through its own host call (cu:774-972) on config 2 and on a config-5 window,
+                     timed beside ours on the same inputs, `reference_cuda == ours` bit for bit, and `reference_cuda vs
+                     reference_cpu` error on configs 2 and 4 (the reference's own CUDA-vs-CPU divergence).
+  e2e_reference_api  the reference's unmodified RaytraceScene<float,float,float>::trace_rays (image_util.cpp:645-772) linked on
+                     the drop-in (oracle/_ref/libvrt_dropin.so), std::vector buffers, configs 2 and 3 at full size, on all GPUs
+                     the process can see; reports what part of the call is ours (inside TraceRaysCu<>::trace_rays_cu) and what is
+                     the reference's own host code above the boundary.
+Everything under oracle/ is used here as the checker / comparator only."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _timed_device(fn, reps=3):
+    import torch
+    best = 1e30
+    out = None
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    return best, out
+
+
+def _err_vs(g_pos, g_dir, g_it, h_pos, h_dir, h_it):
+    same = g_it == h_it
+    if not same.any():
+        return {"max_pos_err_voxel": None, "max_dir_err_rad": None, "step_count_mismatches": int(np.sum(~same))}
+    dp = float(np.abs(g_pos.astype(np.int32) - h_pos.astype(np.int32))[same].max() / 65536.0)
+    a, b = g_dir.astype(np.float64)[same], h_dir.astype(np.float64)[same]
+    cosang = np.sum(a * b, 1) / np.maximum(np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1), 1e-300)
+    return {"max_pos_err_voxel": dp, "max_dir_err_rad": float(np.arccos(np.clip(cosang, -1, 1)).max()), "step_count_mismatches": int(np.sum(~same))}
+
+
+def config_inputs(name, dev):
+    """(label, ior tensor, translucency tensor, pos, dir, iterations, live, min_brightness, parity stride)"""
+    from volumeraytracer_b200 import workloads as W
+    if name == "c2":
+        size = 256
+        pos, d = W.rays_parallel_x(1024, 1024, 30.0, 225.0, x0=2.0)
+        return ("2: 256^3 Luneburg lens, 1M parallel rays", W.ior_luneburg_torch(size, dev), W.clear_translucency_torch((size,) * 3, dev), pos, d, 4096, False, 0, 64)
+    if name == "c3":
+        size = 512
+        pos, d = W.rays_parallel_x(2048, 2048, 4.0, size - 5.0, x0=2.0)
+        return ("3: 512^3 index + live translucency, 4M rays, min-brightness termination", W.ior_sines_torch(size, dev), W.translucency_c3_torch(size, dev),
+                pos, d, 4096, True, 0x40000000, 256)
+    if name == "c4":
+        size = 512
+        pos, d = W.rays_random(8 << 20, 8.0, size - 9.0, 0x5EED0004)
+        return ("4: 512^3 harmonic field, 8M randomly directed rays", W.solve_harmonic_torch(size, dev, inner_radius=64.0, sweeps=300),
+                W.clear_translucency_torch((size,) * 3, dev), pos, d, 4096, False, 0, 512)
+    raise ValueError(name)
+
+
+def run_config(name, dev, with_ref_cuda=False, host_call=True):
+    """One of configs 2-4 at full size on device `dev`.  Returns the result dict (and keeps nothing on the GPU)."""
+    import torch
+    import volumeraytracer_b200 as vrt
+    from oracle import oracle as orc, ref
+    label, ior, tr, pos, d, iterations, live, minb, stride = config_inputs(name, dev)
+    size = ior.shape[0]
+    sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, device=dev.index or 0)
+    del ior, tr
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tpos, tdir)
+    n = pos.shape[0]
+    run = lambda **kw: sc.trace_device(tpos, tdir, [1, 1, 1], minb, iterations, live_translucency=live, **kw)
+    run()                                                                                     # warm-up
+    t, out = _timed_device(run)
+    epos, edir, eit, light = [o.cpu().numpy() for o in out]
+    steps = int(eit.view(np.uint32).astype(np.int64).sum())
+    res = {"config": label, "rays": n, "iterations_cap": iterations, "ray_steps": steps, "g_ray_steps_per_s": steps / t / 1e9, "seconds": t,
+           "mean_steps_per_ray": steps / n, "mode": "device-resident (vrt_trace_device), default options"}
+    # host call with pageable buffers (what a std::vector caller hands over)
+    p_h = tpos.cpu().numpy().view(np.uint32); d_h = tdir.cpu().numpy()
+    if host_call:
+        hp = np.empty_like(p_h); hd = np.empty_like(d_h); hi = np.empty(n, np.uint32); hl = np.empty(n, np.uint32)
+        flags = 1 if live else 0
+        sc.trace_host_buffers(p_h, d_h, [1, 1, 1], minb, iterations, hp, hd, hi, hl, flags=flags)
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter(); sc.trace_host_buffers(p_h, d_h, [1, 1, 1], minb, iterations, hp, hd, hi, hl, flags=flags); best = min(best, time.perf_counter() - t0)
+        res["host_call_pageable"] = {"g_ray_steps_per_s": steps / best / 1e9, "seconds": best,
+                                     "equals_device_run": bool(np.array_equal(hi, eit.view(np.uint32)) and np.array_equal(hp, epos.view(np.uint32)))}
+    # parity on a subsample
+    vol, trc = sc.download_volume()
+    ob = sc._output_sizes
+    sel = np.arange(0, n, stride)
+    p_s = p_h.reshape(-1, 3)[sel]; d_s = d_h.reshape(-1, 3)[sel]
+    kw = dict(translucency=trc if live else None, min_brightness=minb)
+    want = orc.trace(vol, ob, p_s, d_s, [1, 1, 1], iterations, round_mode=orc.ROUND_DEVICE, **kw)
+    g = (epos.view(np.uint32).reshape(-1, 3)[sel], edir.reshape(-1, 3)[sel], eit.view(np.uint32)[sel], light.view(np.uint32)[sel])
+    host = orc.trace(vol, ob, p_s, d_s, [1, 1, 1], iterations, round_mode=orc.ROUND_HOST, **kw)
+    res["parity"] = {"subsample_rays": int(sel.size), "bit_exact": bool(all(np.array_equal(a, b) for a, b in zip(g, want[:4]))),
+                     "oracle": "oracle/vrt_oracle.c ROUND_DEVICE", "vs_reference_cpu_rounding": _err_vs(g[0], g[1], g[2], host[0], host[1], host[2])}
+    # VRT_TRACE_ROUND_HOST: the whole batch with the CPU build's rounding; subsample against the oracle's HOST mode
+    t_h, out_h = _timed_device(lambda: run(round_host=True), reps=2)
+    gh = [o.cpu().numpy() for o in out_h]
+    ghs = (gh[0].view(np.uint32).reshape(-1, 3)[sel], gh[1].reshape(-1, 3)[sel], gh[2].view(np.uint32)[sel], gh[3].view(np.uint32)[sel])
+    res["round_host"] = {"bit_exact_vs_reference_cpu_rounding": bool(all(np.array_equal(a, b) for a, b in zip(ghs, host[:4]))),
+                         "step_count_mismatches": int(np.sum(ghs[2] != host[2])), "g_ray_steps_per_s": int(gh[2].view(np.uint32).astype(np.int64).sum()) / t_h / 1e9,
+                         "oracle": "oracle/vrt_oracle.c ROUND_HOST (bit-identical to the unmodified reference CPU build: tests/test_oracle_vs_reference.py)"}
+    if ref.available():
+        t0 = time.perf_counter()
+        cpu = ref.trace_live(vol, trc if live else None, ob, [1, 1, 1], p_s, d_s, iterations, minb, threads=len(os.sched_getaffinity(0)))
+        dt = time.perf_counter() - t0
+        res["reference_cpu"] = {"g_ray_steps_per_s": int(cpu[2].astype(np.int64).sum()) / dt / 1e9, "threads": len(os.sched_getaffinity(0)), "rays": int(sel.size),
+                                "equals_round_host_gpu": bool(all(np.array_equal(a, b) for a, b in zip(ghs, cpu[:4])))}
+    if with_ref_cuda and not live and ref.available(cuda=True):
+        # the reference's own CUDA build on the same subsample: its distance to its own CPU build is the same as ours
+        planes = [np.ascontiguousarray(vol[:, k]) for k in range(3)]
+        rt = ref.RefTracer(ob, planes, trc, cuda=True)
+        rc = rt.trace(p_s, d_s, [1, 1, 1], 0, iterations)
+        rt.close()
+        res["reference_cuda_on_subsample"] = {"equals_ours": bool(all(np.array_equal(a, b) for a, b in zip(g[:3], rc[:3]))),
+                                              "vs_reference_cpu": _err_vs(rc[0], rc[1], rc[2], host[0], host[1], host[2])}
+        del planes
+    sc.close()
+    del tpos, tdir, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def other_configs(dev, names=("c2", "c3", "c4")):
+    out = {}
+    for nm in names:
+        t0 = time.time()
+        try:
+            out[nm] = run_config(nm, dev, with_ref_cuda=nm in ("c2", "c4"))
+            out[nm]["wall_s"] = round(time.time() - t0, 1)
+        except Exception as e:                                                # a leg that fails must not take the bench line with it
+            out[nm] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+
+def reference_cuda(dev, c5_window=512, size=1024, ray_side=4096, iterations=2048):
+    """The reference's own CUDA kernel through its own host call, beside ours (vrt_trace, pageable buffers), same inputs."""
+    import torch
+    import volumeraytracer_b200 as vrt
+    from oracle import ref
+    from volumeraytracer_b200 import workloads as W
+    if not ref.available(cuda=True):
+        return {"unavailable": "oracle/_ref/libvrt_ref_cuda.so not built"}
+    out = {"kernel": "trace_rays_gpu (cuda_volume_raytracer.cu:397-414), unmodified source, nvcc -gencode arch=compute_100,code=sm_100",
+           "call": "TraceRaysCu<float>::trace_rays_cu<float> (cu:722-972): 32768-ray chunks, per-chunk H2D / launch / cudaDeviceSynchronize / D2H"}
+
+    def beside(label, sc, p_h, d_h, iters):
+        ob = sc._output_sizes
+        vol, trc = sc.download_volume()
+        planes = [np.ascontiguousarray(vol[:, k]) for k in range(3)]
+        del vol
+        rt = ref.RefTracer(ob, planes, trc, cuda=True)
+        rc = rt.trace(p_h, d_h, [1, 1, 1], 0, iters)                                  # warm-up
+        best_r = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter(); rc = rt.trace(p_h, d_h, [1, 1, 1], 0, iters); best_r = min(best_r, time.perf_counter() - t0)
+        rt.close()
+        n = p_h.shape[0]
+        hp = np.empty_like(p_h.reshape(-1)); hd = np.empty_like(d_h.reshape(-1)); hi = np.empty(n, np.uint32); hl = np.empty(n, np.uint32)
+        sc.trace_host_buffers(p_h.reshape(-1), d_h.reshape(-1), [1, 1, 1], 0, iters, hp, hd, hi, hl)
+        best_o = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter(); sc.trace_host_buffers(p_h.reshape(-1), d_h.reshape(-1), [1, 1, 1], 0, iters, hp, hd, hi, hl); best_o = min(best_o, time.perf_counter() - t0)
+        steps = int(hi.astype(np.int64).sum())
+        return {"workload": label, "rays": n, "ray_steps": steps,
+                "reference_cuda_g_ray_steps_per_s": steps / best_r / 1e9, "reference_cuda_seconds": best_r,
+                "ours_host_call_g_ray_steps_per_s": steps / best_o / 1e9, "ours_seconds": best_o, "speedup": best_r / best_o,
+                "bit_exact": bool(np.array_equal(rc[0].reshape(-1), hp) and np.array_equal(rc[1].reshape(-1), hd) and np.array_equal(rc[2], hi))}
+
+    try:
+        label, ior, tr, pos, d, iters, live, minb, stride = config_inputs("c2", dev)
+        sc = vrt.TraceRaysCu.from_ior((ior.shape[0],) * 3, ior, tr, device=dev.index or 0)
+        tp = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d.reshape(-1)).to(dev)
+        sc.normalise_rays_device(tp, td)
+        out["config2"] = beside(label, sc, tp.cpu().numpy().view(np.uint32).reshape(-1, 3), td.cpu().numpy().reshape(-1, 3), iters)
+        sc.close()
+        del ior, tr, tp, td
+        # config-5 window: the centre c5_window^2 rays of the 4096^2 grid through the matching analytic sub-volume (built on the GPU)
+        lo, hi = 2.0, size - 3.0
+        pitch = (hi - lo) / (ray_side - 1)
+        j0 = ray_side // 2 - c5_window // 2
+        y0, y1 = lo + pitch * j0, lo + pitch * (j0 + c5_window - 1)
+        margin = 24
+        ymin, ymax = int(np.floor(y0)) - margin, int(np.ceil(y1)) + margin
+        xmax = min(size, 2 + int(iterations * 0.2578 / 1.15) + margin)
+        k = float(2.0 * np.pi / 256.0)
+        tx = torch.arange(0, xmax, dtype=torch.float32, device=dev) * k
+        ty = torch.arange(ymin, ymax, dtype=torch.float32, device=dev) * k
+        ior = (1.2 + 0.05 * torch.sin(tx)[:, None, None] * torch.cos(ty)[None, :, None] * torch.cos(ty)[None, None, :]).contiguous()
+        tr = W.clear_translucency_torch(tuple(ior.shape), dev)
+        sc = vrt.TraceRaysCu.from_ior(tuple(ior.shape), ior, tr, device=dev.index or 0)
+        pos, d = W.rays_parallel_x(c5_window, c5_window, y0 - ymin, y1 - ymin, x0=2.0)
+        tp = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d.reshape(-1)).to(dev)
+        sc.normalise_rays_device(tp, td)
+        out["config5_window"] = beside("config 5, centre %d^2 of the 4096^2 rays through the matching %dx%dx%d sub-volume, cap %d" % (
+            c5_window, c5_window, ior.shape[0], ior.shape[1], ior.shape[2], iterations), sc, tp.cpu().numpy().view(np.uint32).reshape(-1, 3),
+            td.cpu().numpy().reshape(-1, 3), iterations)
+        sc.close()
+        del ior, tr, tp, td
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+
+def e2e_reference_api(dev, names=("c2", "c3"), n_devices=None):
+    """RaytraceScene<float,float,float> of the UNMODIFIED reference (image_util.cpp) on top of the drop-in.  The process's
+    visible GPUs are all used by the drop-in (VRT_DEVICES limits them)."""
+    import torch
+    from oracle import ref
+    if not ref.available("dropin"):
+        return {"unavailable": "oracle/_ref/libvrt_dropin.so not built"}
+    lib = ref.lib("dropin")
+    for f in ("vrt_dropin_last_ctor_seconds", "vrt_dropin_last_replicate_seconds", "vrt_dropin_last_trace_seconds"):
+        getattr(lib, f).restype = C.c_double
+    if n_devices:
+        os.environ["VRT_DEVICES"] = str(n_devices)
+    out = {"api": "RaytraceScene<float,float,float>::trace_rays (image_util.cpp:645-772, unmodified) -> TraceRaysCu<float>::trace_rays_cu<float> (drop-in)",
+           "devices": n_devices or torch.cuda.device_count()}
+    for nm in names:
+        try:
+            label, ior, tr, pos, d, iters, live, minb, stride = config_inputs(nm, dev)
+            ior_h = ior.cpu().numpy(); tr_h = tr.cpu().numpy().view(np.uint32)
+            del ior, tr
+            torch.cuda.empty_cache()
+            t0 = time.perf_counter()
+            sc = ref.RefScene(ior_h.shape, ior_h, tr_h, which="dropin")
+            t_ctor = time.perf_counter() - t0
+            ctor_ours, repl = lib.vrt_dropin_last_ctor_seconds(), lib.vrt_dropin_last_replicate_seconds()
+            sc.trace(pos[:4096], d[:4096], [1, 1, 1], minb, iters)                        # warm-up (streams, pools)
+            best, ours = 1e30, 0.0
+            for _ in range(2):
+                t0 = time.perf_counter(); got = sc.trace(pos, d, [1, 1, 1], minb, iters); dt = time.perf_counter() - t0
+                if dt < best:
+                    best, ours = dt, lib.vrt_dropin_last_trace_seconds()
+            steps = int(got[2].astype(np.int64).sum())
+            nbytes = int(np.prod(sc.diff_bounds)) * 20
+            out[nm] = {"config": label, "rays": int(pos.shape[0]), "ray_steps": steps,
+                       "call_seconds": best, "g_ray_steps_per_s": steps / best / 1e9,
+                       "inside_our_trace_rays_cu_seconds": ours, "g_ray_steps_per_s_inside_ours": steps / max(ours, 1e-9) / 1e9,
+                       "reference_host_code_and_harness_seconds": best - ours,
+                       "scene_ctor_seconds": t_ctor, "inside_our_ctor_seconds": ctor_ours,
+                       "nvlink_replicate_seconds": repl, "nvlink_replicate_gb_per_s": (nbytes / repl / 1e9) if repl > 0 else None,
+                       "note": "shipped translucency behaviour (the reference compiles the per-step attenuation out, cu:785); "
+                               "call_seconds includes the test harness's std::vector copies of inputs and outputs"}
+            sc.close()
+        except Exception as e:
+            out[nm] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
+if __name__ == "__main__":
+    import torch
+    dev = torch.device("cuda", 0)
+    what = sys.argv[1:] or ["other", "refcuda", "refapi"]
+    if "other" in what:
+        print(json.dumps({"other_configs": other_configs(dev)}), flush=True)
+    if "refcuda" in what:
+        print(json.dumps({"reference_cuda": reference_cuda(dev)}), flush=True)
+    if "refapi" in what:
+        print(json.dumps({"e2e_reference_api": e2e_reference_api(dev)}), flush=True)

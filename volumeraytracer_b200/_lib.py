@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("VRT_B200_LIB") or os.path.join(_HERE, "libvrt_b200.so
 
 VRT_OK, VRT_ERR_INVALID, VRT_ERR_CUDA, VRT_ERR_NOMEM, VRT_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 VRT_F32, VRT_I16, VRT_U32 = 0, 1, 2
-VRT_TRACE_LIVE_TRANSLUCENCY, VRT_TRACE_PATHS = 1, 2
+VRT_TRACE_LIVE_TRANSLUCENCY, VRT_TRACE_PATHS, VRT_TRACE_ROUND_HOST = 1, 2, 4
 VRT_SCENE_BORROW = 1
 VRT_SCENE_LAYOUT_BRICK = 2
 VRT_SCENE_KEEP_I16 = 4
@@ -26,6 +26,8 @@ SYMBOLS = [
     "vrt_scene_create_device", "vrt_scene_create_from_ior", "vrt_scene_destroy", "vrt_scene_info",
     "vrt_scene_download", "vrt_scene_export_device", "vrt_scene_set_option", "vrt_scene_get_option", "vrt_trace", "vrt_trace_device",
     "vrt_normalise_rays_device", "vrt_measure_gather_bandwidth", "vrt_selftest_division", "vrt_launch_count",
+    "vrt_scene_storage_info", "vrt_scene_replicate", "vrt_comm_unique_id", "vrt_comm_create", "vrt_comm_destroy", "vrt_scene_broadcast",
+    "vrt_trace_cap_hit",
 ]
 
 
@@ -68,6 +70,13 @@ def lib():
         L.vrt_normalise_rays_device.argtypes = [vp, u64, vp, vp, i32, C.POINTER(C.c_int64), vp]
         L.vrt_measure_gather_bandwidth.argtypes = [i32, u64, i32, i32, C.POINTER(C.c_double)]
         L.vrt_selftest_division.argtypes = [i32, C.POINTER(C.c_uint64)]
+        L.vrt_scene_storage_info.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_uint), C.POINTER(u64), C.POINTER(vp)]
+        L.vrt_scene_replicate.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(C.c_double)]
+        L.vrt_comm_unique_id.argtypes = [vp]
+        L.vrt_comm_create.argtypes = [C.POINTER(vp), i32, i32, i32, vp]
+        L.vrt_comm_destroy.argtypes = [vp]
+        L.vrt_scene_broadcast.argtypes = [vp, i32, vp, C.POINTER(vp), C.POINTER(C.c_double)]
+        L.vrt_trace_cap_hit.restype = i32
         _lib = L
     return _lib
 

@@ -11,8 +11,12 @@
 //   * no CPU path: the reference traces on the CPU when num_rays <= Options::_minimum_gpu or no device exists
 //     (cu:804-810); here a missing device is a std::runtime_error, the reference's own error convention (cu:54-63)
 //   * multi-GPU: like the reference (cu:676-686, 820-843) the volume lives on every visible device and rays are
-//     split across devices, but as contiguous chunks traced concurrently, not 32 768-ray chunks with a
-//     cudaDeviceSynchronize between them.  VRT_DEVICES=<n> limits the device count.
+//     split across devices, but (a) the volume is uploaded and folded ONCE, on device 0, and replicated device-to-device
+//     over NVLink as a pipelined chain (vrt_scene_replicate) instead of one pageable host upload per device, and (b) rays
+//     are traced as contiguous chunks concurrently, not 32 768-ray chunks with a cudaDeviceSynchronize between them.
+//     VRT_DEVICES=<n> limits the device count.
+//   * the iteration-cap warning (cu:507-515) comes from a flag the marcher sets (vrt_trace_cap_hit), not from a
+//     single-threaded scan over end_iteration.
 //   * VRT_LIVE_TRANSLUCENCY=1 switches on the per-step attenuation / minimum_brightness code that the reference
 //     compiles out at all its call sites (cu:853-938, parameter commented out at cu:785).  Default: off, as shipped.
 // The per-object state is kept behind the reference class's unused `_tex` member (cuda_volume_raytracer.h:70).
@@ -24,6 +28,7 @@
 #include <stdexcept>
 #include <string>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -36,6 +41,10 @@ struct DropinState
 {
     std::vector<vrt_scene *> scenes; // one per device
 };
+
+// measurement hooks for bench.py's e2e_reference_api leg: wall time of the last constructor / trace_rays_cu call inside this
+// object (i.e. what is OURS of a RaytraceScene<>::trace_rays call; the rest is the reference's own host code above the boundary)
+std::atomic<double> g_last_ctor_s{0.0}, g_last_trace_s{0.0}, g_last_replicate_s{0.0};
 
 template <typename T> struct dtype_of;
 template <> struct dtype_of<float>   { static const int value = VRT_F32; };
@@ -84,16 +93,29 @@ TraceRaysCu<DiffType>::TraceRaysCu(std::vector<size_t> const &bounds, std::vecto
     for (auto const *d : diff) planes.push_back(d->data());
     std::unique_ptr<DropinState> st(new DropinState());
     const int ndev = device_budget();
-    for (int dev = 0; dev < ndev; ++dev)
+    const auto t0 = std::chrono::steady_clock::now();
+    // ONE host upload + fold (device 0) ...
+    vrt_scene *first = nullptr;
+    if (vrt_scene_create(&first, 0, dim, b.data(), dtype_of<DiffType>::value, planes.data(), translucency_cropped.data(), VRT_SCENE_DEFAULT) != VRT_OK)
+        raise_last("vrt_scene_create");
+    st->scenes.push_back(first);
+    // ... then device-to-device over NVLink, pipelined down the chain 0 -> 1 -> ... (the reference uploads from the host once
+    // per device, cu:676-686)
+    if (ndev > 1)
     {
-        vrt_scene *s = nullptr;
-        if (vrt_scene_create(&s, dev, dim, b.data(), dtype_of<DiffType>::value, planes.data(), translucency_cropped.data(), VRT_SCENE_DEFAULT) != VRT_OK)
+        std::vector<int> devs;
+        for (int dev = 1; dev < ndev; ++dev) devs.push_back(dev);
+        std::vector<vrt_scene *> rep(devs.size(), nullptr);
+        double secs = 0.0;
+        if (vrt_scene_replicate(first, (int)devs.size(), devs.data(), rep.data(), &secs) != VRT_OK)
         {
-            for (vrt_scene *x : st->scenes) vrt_scene_destroy(x);
-            raise_last("vrt_scene_create");
+            vrt_scene_destroy(first);
+            raise_last("vrt_scene_replicate");
         }
-        st->scenes.push_back(s);
+        g_last_replicate_s = secs;
+        for (vrt_scene *x : rep) st->scenes.push_back(x);
     }
+    g_last_ctor_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     _tex = st.release();
 }
 
@@ -120,6 +142,7 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
     const size_t dim = _output_sizes.size();
     if (dim != 2 && dim != 3) throw std::runtime_error("Illegal dimension");                 // cu:768-771
     const size_t n = start_position.size() / dim;
+    const auto t0 = std::chrono::steady_clock::now();
     // outputs are pre-sized by the caller (image_util.cpp:738-741); path is sized here (cu:791-794)
     if (end_position.size() < n * dim) end_position.resize(n * dim);
     if (end_direction.size() < n * dim) end_direction.resize(n * dim);
@@ -139,6 +162,7 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
     const size_t npieces = std::min<size_t>(ndev * pieces, std::max<size_t>(ndev, (n + 0x7FFFF) / 0x80000));   // at least 2^19 rays per dynamic piece
     std::atomic<size_t> next{0};
     std::vector<std::string> errors(ndev);
+    std::vector<int> cap_hit(ndev, 0);
     const bool dynamic = npieces > ndev;
     auto work = [&](size_t k) {
         // static split: device k traces piece k; dynamic: whatever piece is next
@@ -150,6 +174,9 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
                                scale_vec.data(), minimum_brightness, iterations, flags, end_position.data() + lo * dim, end_direction.data() + lo * dim,
                                end_iteration.data() + lo, remaining_light.data() + lo, trace_paths ? path.data() + lo * dim * iterations : nullptr);
             if (rc != VRT_OK) { errors[k] = vrt_last_error(); return; }
+            const int hit = vrt_trace_cap_hit();     // per calling thread: read it on the thread that traced
+            if (hit < 0) { for (size_t i = lo; i < hi && !cap_hit[k]; ++i) cap_hit[k] |= end_iteration[i] == iterations; }
+            else cap_hit[k] |= hit;
         }
     };
     if (ndev == 1) work(0);
@@ -160,10 +187,17 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
         for (auto &t : pool) t.join();
     }
     for (auto const &e : errors) if (!e.empty()) throw std::runtime_error("vrt_trace: " + e);
-    bool warn = false;                                                                          // cu:507-515
-    for (size_t i = 0; i < n; ++i) warn |= end_iteration[i] == iterations;
+    bool warn = false;                                                                          // cu:507-515: flag set by the marcher
+    for (int h : cap_hit) warn |= h != 0;
     if (warn) std::cout << "Warning, maximum iterations hitted" << std::endl;
     if (opt._loglevel < 0) std::cout << "cpu: 0 gpu: " << ndev << std::endl;                   // cu:948-951
+    g_last_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+extern "C" {
+__attribute__((visibility("default"))) double vrt_dropin_last_ctor_seconds(void) { return g_last_ctor_s; }
+__attribute__((visibility("default"))) double vrt_dropin_last_replicate_seconds(void) { return g_last_replicate_s; }
+__attribute__((visibility("default"))) double vrt_dropin_last_trace_seconds(void) { return g_last_trace_s; }
 }
 
 template class TraceRaysCu<diff_t>;

@@ -17,8 +17,11 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cmath>
 #include <cstring>
@@ -91,11 +94,58 @@ struct vrt_scene
     uint64_t  ior_bounds[3] = {1, 1, 1};
     bool      owns_ior = false;
     int       num_sms = 148;
+    unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: 8 block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
+
+// ---- per-call device buffers: a LIBRARY-OWNED stream-ordered pool per device ---------------------------------------------
+// The reference cudaMalloc/cudaFree's its ray buffers on every call (cu:837-841,958-966).  Here they come from a pool that
+// keeps freed blocks cached between calls (release threshold = unlimited) -- but it is the library's own pool, not the
+// device's default one, so a host application's allocator (e.g. PyTorch's) is not affected by the attribute, and the cache
+// is handed back to the driver (cudaMemPoolTrimTo 0) when the last scene on the device is destroyed.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[64] = {};
+static int g_pool_users[64] = {};
+
+static void pool_acquire(int device)
+{
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    ++g_pool_users[device];
+    if (g_pool[device]) return;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return; }   // pool_alloc falls back to the default pool
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    g_pool[device] = pool;
+}
+
+static void pool_release(int device)
+{
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_users[device] > 0 && --g_pool_users[device] == 0 && g_pool[device])
+    {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(g_pool[device], 0);
+        cudaGetLastError();
+    }
+}
+
+static cudaError_t pool_alloc(void **ptr, size_t bytes, int device, cudaStream_t st)
+{
+    cudaMemPool_t pool = device >= 0 && device < 64 ? g_pool[device] : nullptr;
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, st) : cudaMallocAsync(ptr, bytes, st);
+}
 
 static int check_geometry(int dim, const uint64_t *bounds, uint64_t *nvox)
 {
@@ -128,14 +178,7 @@ static int new_scene(vrt_scene **out, int device, int dim, const uint64_t *bound
     for (int d = 0; d < dim; ++d) s->bounds[d] = bounds[d];
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
-    // per-call ray buffers come from the stream-ordered allocator: keep freed blocks cached in the pool between calls
-    // (the reference cudaMalloc/cudaFree's its ray buffers on every call, cu:837-841,958-966)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-    {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+    pool_acquire(device);
     cudaGetLastError();
     *out = s;
     return VRT_OK;
@@ -230,6 +273,10 @@ static int apply_storage(vrt_scene *s, unsigned flags)
         }
         else cudaGetLastError();       // not enough memory for the wide copy: keep int16
     }
+#ifndef VRT_STUDY
+    if (flags & (VRT_SCENE_LAYOUT_TEXTURE | VRT_SCENE_LAYOUT_PAIR))
+        return fail(VRT_ERR_UNSUPPORTED, "VRT_SCENE_LAYOUT_TEXTURE / _PAIR are layout-study variants: build the library with -DVRT_STUDY (make study)");
+#endif
     if (flags & VRT_SCENE_LAYOUT_TEXTURE)
     {
         if (s->dim != 3 || s->store != VRT_F32 || (flags & VRT_SCENE_LAYOUT_BRICK))
@@ -293,7 +340,7 @@ static int linearise(const vrt_scene *s, void *d_out, cudaStream_t st)
     if (s->paired)      // first voxel of every pair: a strided copy
     {
         void *lin = d_out;
-        if (narrow) VRT_CUDA(cudaMallocAsync(&lin, nelem * 4, st));
+        if (narrow) VRT_CUDA(pool_alloc(&lin, nelem * 4, s->device, st));
         cudaError_t e = cudaMemcpy2DAsync(lin, 16, s->d_volume, 32, 16, s->nvox, cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess && narrow)
         {
@@ -315,7 +362,7 @@ static int linearise(const vrt_scene *s, void *d_out, cudaStream_t st)
     if (s->bricked)
     {
         void *dst = d_out;
-        if (narrow) { VRT_CUDA(cudaMallocAsync(&tmp, nelem * elem_size(s->store), st)); dst = tmp; }
+        if (narrow) { VRT_CUDA(pool_alloc(&tmp, nelem * elem_size(s->store), s->device, st)); dst = tmp; }
         int rc = brick_convert(s, s->d_volume, dst, 0, st);
         if (rc) { if (tmp) cudaFreeAsync(tmp, st); return rc; }
         lin = dst;
@@ -353,7 +400,9 @@ int vrt_scene_destroy(vrt_scene *s)
     if (s->tex_array) cudaFreeArray(s->tex_array);
     if (s->owns) { cudaFree(s->d_volume); cudaFree(s->d_translucency); }
     if (s->owns_ior) cudaFree(s->d_ior);
+    if (s->d_stats) cudaFree(s->d_stats);
     cudaGetLastError();
+    pool_release(s->device);
     delete s;
     return VRT_OK;
 }
@@ -526,9 +575,29 @@ int vrt_scene_info(const vrt_scene *s, int *device, int *dim, uint64_t *bounds, 
     if (dim) *dim = s->dim;
     if (bounds) for (int d = 0; d < s->dim; ++d) bounds[d] = s->bounds[d];
     if (diff_dtype) *diff_dtype = s->dtype;
-    if (d_volume_interleaved) *d_volume_interleaved = s->d_volume;
+    // the staging pointer is only handed out when it IS the reference's layout in the API element type (see the header)
+    const bool plain = s->store == s->dtype && !s->bricked && !s->paired && !s->tex;
+    if (d_volume_interleaved) *d_volume_interleaved = plain ? s->d_volume : nullptr;
     if (d_translucency) *d_translucency = s->d_translucency;
     if (volume_bytes) *volume_bytes = s->nvox * (s->dim + 1) * elem_size(s->dtype);
+    return VRT_OK;
+}
+
+static uint64_t storage_bytes(const vrt_scene *s)
+{
+    if (s->paired) return s->nvox * 32ull;
+    if (s->bricked) return s->nb[0] * s->nb[1] * s->nb[2] * 8ull * 4ull * elem_size(s->store);
+    return s->nvox * (uint64_t)(s->dim + 1) * elem_size(s->store);
+}
+
+int vrt_scene_storage_info(const vrt_scene *s, int *storage_dtype, unsigned *layout_flags, uint64_t *bytes, void **d_storage)
+{
+    if (!s) return fail(VRT_ERR_INVALID, "scene is null");
+    if (storage_dtype) *storage_dtype = s->store;
+    if (layout_flags) *layout_flags = (s->bricked ? VRT_SCENE_LAYOUT_BRICK : 0u) | (s->paired ? VRT_SCENE_LAYOUT_PAIR : 0u) | (s->tex ? VRT_SCENE_LAYOUT_TEXTURE : 0u) |
+                                      (s->dtype == VRT_I16 && s->store == VRT_I16 && s->dim == 3 ? VRT_SCENE_KEEP_I16 : 0u) | (s->owns ? 0u : VRT_SCENE_BORROW);
+    if (bytes) *bytes = storage_bytes(s);
+    if (d_storage) *d_storage = s->d_volume;
     return VRT_OK;
 }
 
@@ -567,7 +636,15 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     if (!s) return fail(VRT_ERR_INVALID, "scene is null");
     switch (key)
     {
-    case VRT_OPT_KERNEL:         if (v < 0 || v > 6 || v == 4 || v == 5) return fail(VRT_ERR_INVALID, "kernel must be 0, 1, 2, 3 or 6 (4/5 are selected by the scene layout)"); s->opt_kernel = v; break;
+    case VRT_OPT_KERNEL:
+        if (v == 10)       // instrumented copy of the default kernel: allocate / zero the block counters
+        {
+            DeviceGuard g(s->device);
+            if (!s->d_stats) VRT_CUDA(cudaMalloc((void **)&s->d_stats, 8 * sizeof(unsigned long long)));
+            VRT_CUDA(cudaMemset(s->d_stats, 0, 8 * sizeof(unsigned long long)));
+        }
+        else if (v < 0 || v > 6 || v == 4 || v == 5) return fail(VRT_ERR_INVALID, "kernel must be 0, 1, 2, 3, 6 or 10 (4/5/7/8/9 are selected implicitly)");
+        s->opt_kernel = v; break;
     case VRT_OPT_BLOCK_THREADS:  if (v < 32 || v > 256 || v % 32) return fail(VRT_ERR_INVALID, "block threads must be a multiple of 32 in [32,256]"); s->opt_block = v; break;
     case VRT_OPT_REFILL:         if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "refill threshold must be 0..32"); s->opt_refill = v; break;
     case VRT_OPT_CHUNK_RAYS:     if (v < 0) return fail(VRT_ERR_INVALID, "chunk must be >= 0"); s->opt_chunk = v; break;
@@ -594,8 +671,352 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_REGION_LOG2: *v = s->opt_region; break;
     case VRT_OPT_REGION_ROUNDS: *v = s->opt_rounds; break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
+    case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
+    case VRT_INFO_STAT_BASE + 0: case VRT_INFO_STAT_BASE + 1: case VRT_INFO_STAT_BASE + 2: case VRT_INFO_STAT_BASE + 3:
+    case VRT_INFO_STAT_BASE + 4: case VRT_INFO_STAT_BASE + 5: case VRT_INFO_STAT_BASE + 6: case VRT_INFO_STAT_BASE + 7:
+    {
+        *v = 0;
+        if (!s->d_stats) break;
+        DeviceGuard g(s->device);
+        unsigned long long h = 0;
+        VRT_CUDA(cudaDeviceSynchronize());
+        VRT_CUDA(cudaMemcpy(&h, s->d_stats + (key - VRT_INFO_STAT_BASE), sizeof h, cudaMemcpyDeviceToHost));
+        *v = (int64_t)h;
+        break;
+    }
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
+    return VRT_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU replication of a staged scene (reference: the per-device host upload loop cu:676-686)
+
+// a scene on `device` with src's geometry, storage description and options, without buffers
+static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
+{
+    vrt_scene *s = nullptr;
+    int rc = new_scene(&s, device, src->dim, src->bounds, src->dtype);
+    if (rc) return rc;
+    s->store = src->store; s->bricked = src->bricked; s->flat_fraction = src->flat_fraction;
+    for (int d = 0; d < 3; ++d) { s->nb[d] = src->nb[d]; s->ior_bounds[d] = src->ior_bounds[d]; }
+    s->ior_dtype = src->ior_dtype;
+    s->opt_kernel = src->opt_kernel.load(); s->opt_block = src->opt_block.load(); s->opt_refill = src->opt_refill.load();
+    s->opt_chunk = src->opt_chunk.load(); s->opt_poll = src->opt_poll.load(); s->opt_max_ctas = src->opt_max_ctas.load();
+    s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
+    *out = s;
+    return VRT_OK;
+}
+
+struct ReplSeg { const char *from; char *to; size_t bytes; };
+
+static uint64_t ior_bytes(const vrt_scene *s)
+{
+    uint64_t n = 1;
+    for (int d = 0; d < s->dim; ++d) n *= s->ior_bounds[d];
+    return n * 4;
+}
+
+// allocate the buffers of a replica and list the (source, destination, bytes) segments to fill
+static int alloc_replica(const vrt_scene *src, vrt_scene *dst, const vrt_scene *from, std::vector<ReplSeg> &segs)
+{
+    DeviceGuard g(dst->device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    VRT_CUDA(cudaMalloc(&dst->d_volume, storage_bytes(src)));
+    dst->owns = true;
+    segs.push_back({(const char *)from->d_volume, (char *)dst->d_volume, (size_t)storage_bytes(src)});
+    if (src->d_translucency)
+    {
+        VRT_CUDA(cudaMalloc((void **)&dst->d_translucency, src->nvox * 4));
+        segs.push_back({(const char *)from->d_translucency, (char *)dst->d_translucency, (size_t)(src->nvox * 4)});
+    }
+    if (src->d_ior)
+    {
+        VRT_CUDA(cudaMalloc(&dst->d_ior, ior_bytes(src)));
+        dst->owns_ior = true;
+        segs.push_back({(const char *)from->d_ior, (char *)dst->d_ior, (size_t)ior_bytes(src)});
+    }
+    return VRT_OK;
+}
+
+static void enable_peer(int a, int b)
+{
+    if (a == b) return;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can)
+    {
+        DeviceGuard g(a);
+        cudaDeviceEnablePeerAccess(b, 0);     // cudaErrorPeerAccessAlreadyEnabled is fine
+    }
+    cudaGetLastError();                        // without peer access cudaMemcpyPeerAsync stages through the host: slower, still correct
+}
+
+// ---- NCCL, loaded at run time -------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi
+{
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("VRT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names)
+        {
+            if (!nm || !*nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);   // a process that already has NCCL mapped (PyTorch) gets that copy
+            if (api.handle) break;
+        }
+        if (!api.handle) return;
+        api.GetUniqueId = (int (*)(NcclId *))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
+        api.CommDestroy = (int (*)(void *))dlsym(api.handle, "ncclCommDestroy");
+        api.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
+        api.GetErrorString = (const char *(*)(int))dlsym(api.handle, "ncclGetErrorString");
+        api.GetVersion = (int (*)(int *))dlsym(api.handle, "ncclGetVersion");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.GetErrorString;
+    });
+    return api;
+}
+} // namespace
+
+struct vrt_comm
+{
+    int device = 0, rank = 0, world = 1;
+    void *comm = nullptr;
+    cudaStream_t stream = nullptr;
+    char *d_hdr = nullptr;       // 256-byte device staging for the scene header
+};
+
+#define VRT_NCCL(call)                                                                                      \
+    do {                                                                                                    \
+        int r__ = (call);                                                                                   \
+        if (r__ != 0) return fail(VRT_ERR_CUDA, std::string("NCCL: ") + nccl().GetErrorString(r__) + " (" #call ")"); \
+    } while (0)
+
+// what vrt_scene_broadcast sends ahead of the payload
+struct SceneHeader
+{
+    uint32_t magic;
+    int32_t  dim, dtype, store, bricked, has_tr, has_ior, ior_dtype;
+    uint64_t bounds[3], nb[3], ior_bounds[3];
+    double   flat_fraction;
+    int64_t  opt[8];
+};
+static_assert(sizeof(SceneHeader) <= 256, "header must fit the staging buffer");
+
+extern "C" {
+
+int vrt_scene_replicate(const vrt_scene *src, int n, const int *devices, vrt_scene **out, double *seconds)
+{
+    if (seconds) *seconds = 0.0;
+    if (!src || n < 0 || (n && (!devices || !out))) return fail(VRT_ERR_INVALID, "null argument");
+    for (int i = 0; i < n; ++i) out[i] = nullptr;
+    if (n == 0) return VRT_OK;
+    if (src->tex || src->paired) return fail(VRT_ERR_UNSUPPORTED, "study layouts are not replicated");
+    int count = 0;
+    VRT_CUDA(cudaGetDeviceCount(&count));
+    for (int i = 0; i < n; ++i) if (devices[i] < 0 || devices[i] >= count) return fail(VRT_ERR_INVALID, "no such CUDA device");
+
+    // the chain: src -> devices[0] -> devices[1] -> ...; hop j copies from chain[j] to chain[j+1]
+    std::vector<const vrt_scene *> chain(1, src);
+    std::vector<std::vector<ReplSeg>> segs(n);
+    int rc = VRT_OK;
+    for (int i = 0; i < n && rc == VRT_OK; ++i)
+    {
+        rc = clone_empty(src, devices[i], &out[i]);
+        if (rc == VRT_OK) rc = alloc_replica(src, out[i], chain.back(), segs[i]);
+        if (rc == VRT_OK) chain.push_back(out[i]);
+    }
+    auto cleanup = [&]() { for (int i = 0; i < n; ++i) { vrt_scene_destroy(out[i]); out[i] = nullptr; } };
+    if (rc) { const std::string msg = g_last_error; cleanup(); return fail(rc, msg); }
+    for (int j = 0; j < n; ++j) { enable_peer(chain[j]->device, chain[j + 1]->device); enable_peer(chain[j + 1]->device, chain[j]->device); }
+
+    constexpr size_t kSlice = 64ull << 20;
+    std::vector<cudaStream_t> st(n, nullptr);
+    std::vector<std::vector<cudaEvent_t>> ev(n);
+    cudaError_t e = cudaSuccess;
+    size_t nslices = 0;
+    for (const ReplSeg &g : segs[0]) nslices += (g.bytes + kSlice - 1) / kSlice;
+    for (int j = 0; j < n && e == cudaSuccess; ++j)
+    {
+        DeviceGuard g(chain[j]->device);                       // the sender pushes
+        e = cudaStreamCreateWithFlags(&st[j], cudaStreamNonBlocking);
+        if (j + 1 < n) { ev[j].resize(nslices, nullptr); for (size_t k = 0; k < nslices && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[j][k], cudaEventDisableTiming); }
+    }
+    { DeviceGuard g(src->device); if (e == cudaSuccess) e = cudaDeviceSynchronize(); }
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t k = 0;
+    for (size_t sg = 0; sg < segs[0].size() && e == cudaSuccess; ++sg)
+        for (size_t off = 0; off < segs[0][sg].bytes && e == cudaSuccess; off += kSlice, ++k)
+        {
+            const size_t len = std::min(kSlice, segs[0][sg].bytes - off);
+            for (int j = 0; j < n && e == cudaSuccess; ++j)    // slice k travels down the chain; hop j waits for hop j-1's copy of the same slice
+            {
+                DeviceGuard g(chain[j]->device);
+                if (j > 0) e = cudaStreamWaitEvent(st[j], ev[j - 1][k], 0);
+                if (e == cudaSuccess) e = cudaMemcpyPeerAsync(segs[j][sg].to + off, chain[j + 1]->device, segs[j][sg].from + off, chain[j]->device, len, st[j]);
+                if (e == cudaSuccess && j + 1 < n) e = cudaEventRecord(ev[j][k], st[j]);
+            }
+        }
+    for (int j = 0; j < n; ++j) if (st[j]) { cudaError_t e2 = cudaStreamSynchronize(st[j]); if (e == cudaSuccess) e = e2; }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int j = 0; j < n; ++j)
+    {
+        for (cudaEvent_t x : ev[j]) if (x) cudaEventDestroy(x);
+        if (st[j]) cudaStreamDestroy(st[j]);
+    }
+    if (e != cudaSuccess) { cleanup(); cudaGetLastError(); return fail(VRT_ERR_CUDA, std::string("replication failed: ") + cudaGetErrorString(e)); }
+    g_launches += 0;
+    if (seconds) *seconds = dt;
+    return VRT_OK;
+}
+
+int vrt_comm_unique_id(void *id)
+{
+    if (!id) return fail(VRT_ERR_INVALID, "id is null");
+    if (!nccl().ok) return fail(VRT_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded");
+    NcclId u;
+    VRT_NCCL(nccl().GetUniqueId(&u));
+    memcpy(id, &u, sizeof u);
+    return VRT_OK;
+}
+
+int vrt_comm_create(vrt_comm **out, int device, int rank, int world, const void *id)
+{
+    if (!out || !id) return fail(VRT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(VRT_ERR_INVALID, "bad rank / world");
+    if (!nccl().ok) return fail(VRT_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    vrt_comm *c = new vrt_comm();
+    c->device = device; c->rank = rank; c->world = world;
+    NcclId u;
+    memcpy(&u, id, sizeof u);
+    int r = nccl().CommInitRank(&c->comm, world, u, rank);
+    if (r != 0) { delete c; return fail(VRT_ERR_CUDA, std::string("NCCL: ") + nccl().GetErrorString(r) + " (ncclCommInitRank)"); }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    e = e == cudaSuccess ? cudaMalloc((void **)&c->d_hdr, 256) : e;
+    // warm-up: NCCL connects its channels lazily on the first collective; do that here, not inside the first scene broadcast
+    void *warm = nullptr;
+    e = e == cudaSuccess ? cudaMalloc(&warm, 8u << 20) : e;
+    if (e == cudaSuccess)
+    {
+        r = nccl().Broadcast(c->d_hdr, c->d_hdr, 4, 0, 0, c->comm, c->stream);
+        if (r == 0) r = nccl().Broadcast(warm, warm, 8u << 20, 0, 0, c->comm, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+    }
+    if (warm) cudaFree(warm);
+    if (e != cudaSuccess || r != 0)
+    {
+        const std::string msg = r != 0 ? std::string("NCCL: ") + nccl().GetErrorString(r) : std::string(cudaGetErrorString(e));
+        vrt_comm_destroy(c);
+        cudaGetLastError();
+        return fail(VRT_ERR_CUDA, msg);
+    }
+    *out = c;
+    return VRT_OK;
+}
+
+int vrt_comm_destroy(vrt_comm *c)
+{
+    if (!c) return VRT_OK;
+    DeviceGuard g(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    if (c->d_hdr) cudaFree(c->d_hdr);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return VRT_OK;
+}
+
+int vrt_scene_broadcast(vrt_comm *c, int root, vrt_scene *src, vrt_scene **out, double *seconds)
+{
+    if (seconds) *seconds = 0.0;
+    if (!c || !out) return fail(VRT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (root < 0 || root >= c->world) return fail(VRT_ERR_INVALID, "bad root");
+    const bool is_root = c->rank == root;
+    if (is_root && !src) return fail(VRT_ERR_INVALID, "the root rank needs a scene");
+    if (is_root && (src->tex || src->paired)) return fail(VRT_ERR_UNSUPPORTED, "study layouts are not replicated");
+    if (is_root && src->device != c->device) return fail(VRT_ERR_INVALID, "the scene is not on the communicator's device");
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    SceneHeader h;
+    memset(&h, 0, sizeof h);
+    if (is_root)
+    {
+        h.magic = 0x56525442u; h.dim = src->dim; h.dtype = src->dtype; h.store = src->store; h.bricked = src->bricked;
+        h.has_tr = src->d_translucency != nullptr; h.has_ior = src->d_ior != nullptr; h.ior_dtype = src->ior_dtype;
+        for (int d = 0; d < 3; ++d) { h.bounds[d] = src->bounds[d]; h.nb[d] = src->nb[d]; h.ior_bounds[d] = src->ior_bounds[d]; }
+        h.flat_fraction = src->flat_fraction;
+        h.opt[0] = src->opt_kernel; h.opt[1] = src->opt_block; h.opt[2] = src->opt_refill; h.opt[3] = src->opt_chunk;
+        h.opt[4] = src->opt_poll; h.opt[5] = src->opt_max_ctas; h.opt[6] = src->opt_region; h.opt[7] = src->opt_rounds;
+        VRT_CUDA(cudaMemcpyAsync(c->d_hdr, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    }
+    VRT_NCCL(nccl().Broadcast(c->d_hdr, c->d_hdr, 256, 0, root, c->comm, c->stream));
+    if (!is_root) VRT_CUDA(cudaMemcpyAsync(&h, c->d_hdr, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(cudaStreamSynchronize(c->stream));
+    if (h.magic != 0x56525442u) return fail(VRT_ERR_INVALID, "scene header did not arrive (root has no scene?)");
+
+    vrt_scene *s = src;
+    if (!is_root)
+    {
+        vrt_scene proto;                       // geometry carrier for clone_empty / alloc_replica
+        proto.dim = h.dim; proto.dtype = h.dtype; proto.store = h.store; proto.bricked = h.bricked != 0; proto.flat_fraction = h.flat_fraction;
+        proto.ior_dtype = h.ior_dtype; proto.nvox = 1;
+        for (int d = 0; d < 3; ++d) { proto.bounds[d] = h.bounds[d]; proto.nb[d] = h.nb[d]; proto.ior_bounds[d] = h.ior_bounds[d]; }
+        for (int d = 0; d < h.dim; ++d) proto.nvox *= h.bounds[d];
+        proto.opt_kernel = h.opt[0]; proto.opt_block = h.opt[1]; proto.opt_refill = h.opt[2]; proto.opt_chunk = h.opt[3];
+        proto.opt_poll = h.opt[4]; proto.opt_max_ctas = h.opt[5]; proto.opt_region = h.opt[6]; proto.opt_rounds = h.opt[7];
+        proto.d_translucency = h.has_tr ? (uint32_t *)1 : nullptr;      // only tested for presence
+        proto.d_ior = h.has_ior ? (void *)1 : nullptr;
+        int rc = clone_empty(&proto, c->device, &s);
+        std::vector<ReplSeg> unused;
+        if (rc == VRT_OK) rc = alloc_replica(&proto, s, &proto, unused);
+        proto.d_translucency = nullptr; proto.d_ior = nullptr;
+        if (rc) { const std::string msg = g_last_error; vrt_scene_destroy(s); return fail(rc, msg); }
+    }
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t e = cudaEventCreate(&a);
+    e = e == cudaSuccess ? cudaEventCreate(&b) : e;
+    e = e == cudaSuccess ? cudaEventRecord(a, c->stream) : e;
+    int r = 0;
+    if (e == cudaSuccess)
+    {
+        r = nccl().Broadcast(s->d_volume, s->d_volume, (size_t)storage_bytes(s), 0, root, c->comm, c->stream);       // in place on every rank
+        if (r == 0 && h.has_tr) r = nccl().Broadcast(s->d_translucency, s->d_translucency, (size_t)(s->nvox * 4), 0, root, c->comm, c->stream);
+        if (r == 0 && h.has_ior) r = nccl().Broadcast(s->d_ior, s->d_ior, (size_t)ior_bytes(s), 0, root, c->comm, c->stream);
+        e = cudaEventRecord(b, c->stream);
+        e = e == cudaSuccess ? cudaStreamSynchronize(c->stream) : e;
+    }
+    float ms = 0.0f;
+    if (e == cudaSuccess && r == 0) cudaEventElapsedTime(&ms, a, b);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (e != cudaSuccess || r != 0)
+    {
+        const std::string msg = r != 0 ? std::string("NCCL: ") + nccl().GetErrorString(r) + " (ncclBroadcast)" : std::string(cudaGetErrorString(e));
+        if (!is_root) vrt_scene_destroy(s);
+        cudaGetLastError();
+        return fail(VRT_ERR_CUDA, msg);
+    }
+    if (seconds) *seconds = ms * 1e-3;
+    *out = s;
     return VRT_OK;
 }
 
@@ -632,27 +1053,42 @@ static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, 
 template <typename VoxT, bool DIR_I16, bool LIVE>
 static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path, int kver, int block, cudaStream_t st)
 {
-    if (path) return kver == 7 ? launch3<VoxT, DIR_I16, LIVE, true, 7>(s, p, block, st)
-                               : launch3<VoxT, DIR_I16, LIVE, true, 2>(s, p, block, st);   // polyline output is store-bound: one variant per layout
+#ifdef VRT_STUDY
+    if (path && kver == 7) return launch3<VoxT, DIR_I16, LIVE, true, 7>(s, p, block, st);
+#endif
+    if (path) return kver == 8 ? launch3<VoxT, DIR_I16, LIVE, true, 8>(s, p, block, st)
+                               : launch3<VoxT, DIR_I16, LIVE, true, 2>(s, p, block, st);   // polyline output is store-bound: one variant per rounding
     switch (kver)
     {
     case 1: return launch3<VoxT, DIR_I16, LIVE, false, 1>(s, p, block, st);
     case 2: return launch3<VoxT, DIR_I16, LIVE, false, 2>(s, p, block, st);
     case 4: return launch3<VoxT, DIR_I16, LIVE, false, 4>(s, p, block, st);
-    case 5: return launch3<VoxT, DIR_I16, LIVE, false, 5>(s, p, block, st);
     case 6: return launch3<VoxT, DIR_I16, LIVE, false, 6>(s, p, block, st);
+    case 8: return launch3<VoxT, DIR_I16, LIVE, false, 8>(s, p, block, st);
+#ifdef VRT_STUDY
+    case 5: return launch3<VoxT, DIR_I16, LIVE, false, 5>(s, p, block, st);
     case 7: return launch3<VoxT, DIR_I16, LIVE, false, 7>(s, p, block, st);
+#endif
     case 9: return launch3<VoxT, DIR_I16, LIVE, false, 9>(s, p, block, st);
+    case 10: return launch3<float, false, false, false, 10>(s, p, block, st);      // enqueue_march only selects it for this instantiation
     default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
     }
 }
 
 template <typename VoxT, bool DIR_I16, bool LIVE>
-static cudaError_t launch2_k(const MarchParams &p, bool path, int block, cudaStream_t st)
+static cudaError_t launch2_k(const MarchParams &p, bool path, bool hostr, int block, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((p.n + block - 1) / block);
-    if (path) march2_kernel<VoxT, DIR_I16, LIVE, true><<<grid, block, 0, st>>>(p);
-    else      march2_kernel<VoxT, DIR_I16, LIVE, false><<<grid, block, 0, st>>>(p);
+    if (hostr)
+    {
+        if (path) march2_kernel<VoxT, DIR_I16, LIVE, true, true><<<grid, block, 0, st>>>(p);
+        else      march2_kernel<VoxT, DIR_I16, LIVE, false, true><<<grid, block, 0, st>>>(p);
+    }
+    else
+    {
+        if (path) march2_kernel<VoxT, DIR_I16, LIVE, true, false><<<grid, block, 0, st>>>(p);
+        else      march2_kernel<VoxT, DIR_I16, LIVE, false, false><<<grid, block, 0, st>>>(p);
+    }
     ++g_launches;
     return cudaGetLastError();
 }
@@ -665,8 +1101,9 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
         if (dir_i16) return live ? launch3_k<VoxT, true, true>(s, p, path, kver, block, st) : launch3_k<VoxT, true, false>(s, p, path, kver, block, st);
         return live ? launch3_k<VoxT, false, true>(s, p, path, kver, block, st) : launch3_k<VoxT, false, false>(s, p, path, kver, block, st);
     }
-    if (dir_i16) return live ? launch2_k<VoxT, true, true>(p, path, block, st) : launch2_k<VoxT, true, false>(p, path, block, st);
-    return live ? launch2_k<VoxT, false, true>(p, path, block, st) : launch2_k<VoxT, false, false>(p, path, block, st);
+    const bool hostr = kver == 8;
+    if (dir_i16) return live ? launch2_k<VoxT, true, true>(p, path, hostr, block, st) : launch2_k<VoxT, true, false>(p, path, hostr, block, st);
+    return live ? launch2_k<VoxT, false, true>(p, path, hostr, block, st) : launch2_k<VoxT, false, false>(p, path, hostr, block, st);
 }
 
 // ---- region mode (vrt_region.cuh): sort by region, march region by region, all on the caller's stream ---------------
@@ -704,7 +1141,7 @@ static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool
     const size_t o_k0 = o_light + al(n * 4), o_k1 = o_k0 + al(n * 2), o_o0 = o_k1 + al(n * 2), o_o1 = o_o0 + al(n * 4);
     const size_t o_cnt = o_o1 + al(n * 4), o_cub = o_cnt + 256, total = o_cub + al(cub_bytes);
     char *ws = nullptr;
-    VRT_CUDA(cudaMallocAsync((void **)&ws, total, st));
+    VRT_CUDA(pool_alloc((void **)&ws, total, s->device, st));
     RegionParams rp;
     rp.m = mp;
     rp.m.counter = (unsigned long long *)(ws + o_cnt);
@@ -760,11 +1197,13 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     return VRT_OK;
 }
 
-// enqueue one marcher launch on `st`; `counter` is an 8-byte device scratch (zeroed here) or null for static mode
+// enqueue one marcher launch on `st`; `scratch` is a 16-byte device scratch (zeroed here: [0] = refill counter, [1] = cap flag,
+// read back by vrt_trace) or null for static mode without a cap flag
 static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
                          uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
-                         uint32_t *d_light, uint32_t *d_path, unsigned long long *counter, cudaStream_t st, int region_log2)
+                         uint32_t *d_light, uint32_t *d_path, unsigned long long *scratch, cudaStream_t st, int region_log2)
 {
+    unsigned long long *counter = scratch && s->opt_refill.load() > 0 && s->dim == 3 ? scratch : nullptr;
     if (n == 0) return VRT_OK;
     MarchParams p;
     p.volume = s->d_volume; p.translucency = s->d_translucency;
@@ -792,6 +1231,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.one[0] = p.one[1] = 1.0f;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
+    p.cap_flag = scratch ? (uint32_t *)(scratch + 1) : nullptr;
     int kver = (int)s->opt_kernel.load();
     if (kver == 0) kver = 3;   // 6 (empty-space fast path) stays opt-in: it wins on coherent bundles through mostly empty volumes
                                // (config 1: 25x, config 2: +7 %) and loses where flat and curved cells mix inside a warp
@@ -802,10 +1242,27 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.nby = (uint32_t)s->nb[1]; p.nbz = (uint32_t)s->nb[2];
     const int block = (int)s->opt_block.load();
     const bool live = flags & VRT_TRACE_LIVE_TRANSLUCENCY, path = flags & VRT_TRACE_PATHS, di16 = dir_dtype == VRT_I16;
+    if (kver == 10)    // the instrumented copy exists for the default instantiation only; anything else runs the default kernel
+    {
+        const bool fits = s->dim == 3 && s->store == VRT_F32 && !di16 && !live && !path && !s->bricked && !s->tex && !s->paired &&
+                          p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f && s->d_stats;
+        if (!fits) kver = 3;
+    }
+    p.stats = kver == 10 ? s->d_stats : nullptr;
     if (kver == 3 && !path && p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f) kver = 9;   // unit invscale: two multiplies fewer per step, same bits
-    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex)
+    const bool hostr = flags & VRT_TRACE_ROUND_HOST;
+    if (hostr)
+    {
+        if (s->bricked || s->tex || s->paired) return fail(VRT_ERR_UNSUPPORTED, "VRT_TRACE_ROUND_HOST needs the linear layout");
+        kver = 8;
+    }
+    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex && !hostr)
+    {
+        if (scratch) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+    }
+    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex && !hostr)
         return enqueue_march_regions(s, p, di16, live, st, region_log2);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
-    if (p.refill) VRT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    if (scratch) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
     cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
                                         : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
     VRT_CUDA(e);
@@ -880,6 +1337,13 @@ struct ThreadCtx
     ~ThreadCtx() { release(); }   // at process exit the runtime may already be unloading: the calls then fail harmlessly
 };
 static thread_local ThreadCtx t_ctx;
+static thread_local int t_cap_hit = -1;     // vrt_trace_cap_hit(): 1 / 0 / -1 (unknown)
+
+static uint64_t region_count(const vrt_scene *s, int k)
+{
+    const uint64_t e = 1ull << k;
+    return ((s->bounds[0] + e - 1) / e) * ((s->bounds[1] + e - 1) / e) * ((s->bounds[2] + e - 1) / e);
+}
 
 extern "C" {
 
@@ -892,12 +1356,12 @@ int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void
     DeviceGuard g(s->device);
     if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    unsigned long long *counter = nullptr;
+    unsigned long long *scratch = nullptr;
     const bool refill = s->opt_refill.load() > 0 && s->dim == 3;
-    if (refill) VRT_CUDA(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
+    if (refill) VRT_CUDA(pool_alloc((void **)&scratch, 2 * sizeof(unsigned long long), s->device, st));
     const int region = (int)std::max<int64_t>(0, s->opt_region.load());      // device buffers: region mode only on request
-    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, counter, st, region);
-    if (counter) cudaFreeAsync(counter, st);
+    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, scratch, st, region);
+    if (scratch) cudaFreeAsync(scratch, st);
     return rc;
 }
 
@@ -912,14 +1376,19 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     const int dim = s->dim;
     const size_t ds = elem_size(dir_dtype);
     const bool want_path = flags & VRT_TRACE_PATHS;
-    const bool refill = s->opt_refill.load() > 0 && dim == 3;
     if (!t_ctx.ensure(s->device)) return fail(VRT_ERR_CUDA, "could not create the per-thread streams / staging buffers");
     // region mode: on request (5..9), never (-1), or -- default 0 -- decided per batch by the host-side coherence probe
     int region = (int)s->opt_region.load();
     if (region == 0 && dim == 3 && !want_path && !s->bricked && !s->tex && n >= (1u << 18) &&
         s->nvox * 4 * elem_size(s->store) > (96ull << 20) && batch_is_incoherent(n, dim, pos, dir, dir_dtype))
+    {
+        // automatic choice: the region key is 16 bits, so thin, wide volumes need larger regions -- or stay with the single launch
         region = 6;
+        while (region <= 9 && region_count(s, region) >= kRegionDone) ++region;
+        if (region > 9) region = 0;
+    }
     if (region < 0) region = 0;
+    t_cap_hit = -1;
 
     // Small batches (latency path): one packed H2D, one launch, one packed D2H through pinned staging -- 2 copies instead
     // of 6, no allocation.  Static ray-to-thread mapping (the grid covers the batch at once, nothing to refill).
@@ -943,6 +1412,9 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             memcpy(edir, h + b_pos, (size_t)n * dim * ds);
             memcpy(eit, h + b_pos + b_dir, b_u32);
             memcpy(light, h + b_pos + b_dir + b_u32, b_u32);
+            int cap = 0;
+            for (uint64_t i = 0; i < n; ++i) cap |= eit[i] == iterations;
+            t_cap_hit = cap;
             return VRT_OK;
         }
     }
@@ -968,7 +1440,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     // still overlap the march (config 5 through pageable numpy arrays: 171 -> see DESIGN.md section 5).
     constexpr size_t kWindowBytes = 4ull << 30;
     constexpr size_t kWindowChunks = ThreadCtx::kEvents / 2;
-    struct Pending { char *buf; uint64_t off, m; size_t o_dir, o_eit, o_light, o_path, b_path, bytes; cudaEvent_t marched; };
+    struct Pending { char *buf; uint64_t off, m; size_t o_dir, o_eit, o_light, o_path, b_path, bytes, o_flag; uint32_t *flag_slot; cudaEvent_t marched; };
     std::deque<Pending> pending;
     size_t pending_bytes = 0;
     int result = VRT_OK;
@@ -989,9 +1461,12 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             note(cudaMemcpyAsync(eit + c.off, c.buf + c.o_eit, b_u32, cudaMemcpyDeviceToHost, q));
             note(cudaMemcpyAsync(light + c.off, c.buf + c.o_light, b_u32, cudaMemcpyDeviceToHost, q));
             if (want_path) note(cudaMemcpyAsync(path + c.off * iterations * dim, c.buf + c.o_path, c.b_path, cudaMemcpyDeviceToHost, q));
+            if (c.flag_slot) note(cudaMemcpyAsync(c.flag_slot, c.buf + c.o_flag, 4, cudaMemcpyDeviceToHost, q));   // pinned: asynchronous
         }
         cudaFreeAsync(c.buf, q);
     };
+    uint32_t *const flag_slots = (uint32_t *)t_ctx.h_stage;
+    constexpr uint64_t kFlagSlots = ThreadCtx::kSmallBytes / 4;
 
     uint64_t index = 0;
     for (uint64_t off = 0; off < n && result == VRT_OK; off += chunk, ++index)
@@ -1005,12 +1480,15 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         c.o_dir = (b_pos + 255) & ~(size_t)255; c.o_eit = (c.o_dir + b_dir + 255) & ~(size_t)255; c.o_light = (c.o_eit + b_u32 + 255) & ~(size_t)255;
         const size_t o_cnt = (c.o_light + b_u32 + 255) & ~(size_t)255;
         c.o_path = o_cnt + 256;
+        c.o_flag = o_cnt + 8;
+        c.flag_slot = index < kFlagSlots ? flag_slots + index : nullptr;
+        if (c.flag_slot) *c.flag_slot = 0;
         c.b_path = want_path ? (size_t)m * iterations * dim * 4 : 0;
         c.bytes = c.o_path + c.b_path;
         while (!pending.empty() && (pending_bytes + c.bytes > kWindowBytes || pending.size() >= kWindowChunks)) drain_front();
         if (result != VRT_OK) break;
         c.buf = nullptr;
-        note(cudaMallocAsync((void **)&c.buf, c.bytes, t_ctx.in));
+        note(pool_alloc((void **)&c.buf, c.bytes, s->device, t_ctx.in));
         if (result != VRT_OK) break;
         cudaEvent_t staged = t_ctx.ev[(index * 2) % ThreadCtx::kEvents];
         c.marched = t_ctx.ev[(index * 2 + 1) % ThreadCtx::kEvents];
@@ -1024,7 +1502,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             uint32_t *d_pos = (uint32_t *)c.buf; void *d_dir = c.buf + c.o_dir;
             int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, (uint32_t *)(c.buf + c.o_eit),
                                     (uint32_t *)(c.buf + c.o_light), want_path ? (uint32_t *)(c.buf + c.o_path) : nullptr,
-                                    refill ? (unsigned long long *)(c.buf + o_cnt) : nullptr, q, region);
+                                    (unsigned long long *)(c.buf + o_cnt), q, region);
             if (rc2 && result == VRT_OK) result = rc2;
         }
         note(cudaEventRecord(c.marched, q));
@@ -1034,8 +1512,16 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     while (!pending.empty()) drain_front();
     cudaStream_t all[4] = {t_ctx.in, t_ctx.st[0], t_ctx.st[1], t_ctx.out};
     for (cudaStream_t q : all) note(cudaStreamSynchronize(q));
+    if (result == VRT_OK && index <= kFlagSlots)
+    {
+        uint32_t any = 0;
+        for (uint64_t i = 0; i < index; ++i) any |= flag_slots[i];
+        t_cap_hit = any ? 1 : 0;
+    }
     return result;
 }
+
+int vrt_trace_cap_hit(void) { return t_cap_hit; }
 
 int vrt_normalise_rays_device(vrt_scene *s, uint64_t n, uint32_t *d_pos, void *d_dir, int dir_dtype, int64_t *first_bad_ray, void *cuda_stream)
 {
@@ -1049,7 +1535,7 @@ int vrt_normalise_rays_device(vrt_scene *s, uint64_t n, uint32_t *d_pos, void *d
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     unsigned long long *d_flags = nullptr;
-    VRT_CUDA(cudaMallocAsync((void **)&d_flags, 16, st));
+    VRT_CUDA(pool_alloc((void **)&d_flags, 16, s->device, st));
     VRT_CUDA(cudaMemsetAsync(d_flags, 0xFF, 16, st));
     NormParams np;
     np.dim = s->dim; np.n = n;

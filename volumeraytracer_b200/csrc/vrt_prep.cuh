@@ -192,7 +192,10 @@ struct NormParams
 __device__ __forceinline__ unsigned long long corner_index(const NormParams &p, const uint32_t *pos, int k)
 {
     unsigned long long idx = 0;
-    for (int d = 0; d < p.dim; ++d) idx = idx * p.ib[d] + (pos[d] >> 16) + (unsigned)((k >> (p.dim - 1 - d)) & 1);
+    // A ray in the last half voxel of an axis passes the reference's range check (image_util.cpp:686) and then has
+    // (pos >> 16) + 1 == bounds: the reference's host interpolator reads past the volume there.  The upper corner is clamped
+    // to the last voxel instead (such a ray retires on the marcher's first bounds test, its direction scale is irrelevant).
+    for (int d = 0; d < p.dim; ++d) idx = idx * p.ib[d] + min((pos[d] >> 16) + (unsigned)((k >> (p.dim - 1 - d)) & 1), p.ib[d] - 1u);
     return idx;
 }
 

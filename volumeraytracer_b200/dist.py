@@ -7,6 +7,9 @@ Rays are independent, so the path shards with no per-step collective (SURVEY.md 
   * the ray batch is split into `world` contiguous chunks (the reference hands out 32 768-ray chunks dynamically,
     cu:820-821); every rank marches its chunk and results land at the rays' original indices.
 """
+import os
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -64,3 +67,42 @@ def gather_results(n_rays, per_ray, local, dst=0, group=None):
         return torch.cat([parts[r][:sizes[r] * per_ray] for r in range(world)])
     dist.gather(buf, None, dst=dst, group=group)
     return None
+
+
+class SharedBatch:
+    """ONE ray batch in ONE set of host arrays shared by all ranks of the node (a file per array under /dev/shm, mapped by
+    every rank).  This is how one-process-per-GPU ranks serve the reference's calling convention -- one caller-owned batch,
+    results written in place at the rays' original indices (cuda_volume_raytracer.cu:804-821 splits one batch over the
+    devices the same way) -- without a gather: rank r traces `slices(r)` of the shared arrays through vrt_trace and the
+    results are where the caller expects them.  Arrays: pos [n*dim] u32, dir [n*dim] f32|i16, epos, edir, eit [n], light [n]."""
+
+    FIELDS = ("pos", "dir", "epos", "edir", "eit", "light")
+
+    def __init__(self, tag, n_rays, dim, dir_dtype, create, directory="/dev/shm"):
+        self.n, self.dim, self.dir_dtype = int(n_rays), int(dim), np.dtype(dir_dtype)
+        self.paths = {f: os.path.join(directory, "%s_%s.bin" % (tag, f)) for f in self.FIELDS}
+        shapes = {"pos": (self.n * dim, np.uint32), "dir": (self.n * dim, self.dir_dtype), "epos": (self.n * dim, np.uint32),
+                  "edir": (self.n * dim, self.dir_dtype), "eit": (self.n, np.uint32), "light": (self.n, np.uint32)}
+        self.arrays = {}
+        for f, (count, dt) in shapes.items():
+            if create:
+                with open(self.paths[f], "wb") as fh:
+                    fh.truncate(max(count, 1) * np.dtype(dt).itemsize)
+            self.arrays[f] = np.memmap(self.paths[f], dtype=dt, mode="r+", shape=(count,))
+        self.owner = bool(create)
+
+    def slices(self, world, rank):
+        """rank's views (pos, dir, epos, edir, eit, light) of the shared arrays: its contiguous chunk, no copy."""
+        lo, hi = chunk_bounds(self.n, world, rank)
+        d = self.dim
+        a = self.arrays
+        return (a["pos"][lo * d:hi * d], a["dir"][lo * d:hi * d], a["epos"][lo * d:hi * d], a["edir"][lo * d:hi * d], a["eit"][lo:hi], a["light"][lo:hi])
+
+    def close(self):
+        self.arrays = {}
+        if self.owner:
+            for p in self.paths.values():
+                try:
+                    os.unlink(p)
+                except OSError:
+                    pass

@@ -112,6 +112,21 @@ class TraceRaysCu:
         self._output_sizes = [int(b) for b in bounds[:dim.value]]      # public member in the reference (h:73)
         self.volume_ptr, self.translucency_ptr, self.volume_bytes = dvol.value, dtr.value, nbytes.value
 
+    def storage_info(self):
+        """(storage dtype, layout flags, bytes, device address) of the staged copy (vrt_scene_storage_info)."""
+        dt, fl, nb, ptr = C.c_int(), C.c_uint(), C.c_uint64(), C.c_void_p()
+        L.check(L.lib().vrt_scene_storage_info(self._h, C.byref(dt), C.byref(fl), C.byref(nb), C.byref(ptr)))
+        return dt.value, fl.value, nb.value, ptr.value
+
+    def replicate(self, devices):
+        """In-process multi-GPU replication over NVLink peer copies (vrt_scene_replicate; reference: the per-device host
+        upload loop cu:676-686).  Returns ([TraceRaysCu on devices[i]], seconds)."""
+        devs = (C.c_int * len(devices))(*devices)
+        outs = (C.c_void_p * len(devices))()
+        secs = C.c_double(0.0)
+        L.check(L.lib().vrt_scene_replicate(self._h, len(devices), devs, outs, C.byref(secs)))
+        return [TraceRaysCu(None, None, None, _handle=C.c_void_p(h)) for h in outs], secs.value
+
     def download_volume(self):
         """Host copy of the staged interleaved volume [nvox, dim+1] and of the cropped translucency plane."""
         nvox = int(np.prod(self._output_sizes))
@@ -149,7 +164,7 @@ class TraceRaysCu:
 
     # -- the path -----------------------------------------------------------------------------------
     def trace_rays_cu(self, start_position, start_direction, scale_vec, minimum_brightness, iterations,
-                      trace_paths=False, opt=None, live_translucency=False):
+                      trace_paths=False, opt=None, live_translucency=False, round_host=False):
         """Returns (end_position, end_direction, end_iteration, remaining_light, path).  Coordinates are
         cropped-volume 16.16 (the reference boundary's convention).  live_translucency=False reproduces the shipped
         behaviour, where the per-step attenuation is compiled out and minimum_brightness is ignored (cu:785)."""
@@ -167,7 +182,8 @@ class TraceRaysCu:
         epos = np.empty_like(pos); edir = np.empty_like(d)
         eit = np.empty(n, dtype=np.uint32); light = np.empty(n, dtype=np.uint32)
         path = np.empty(n * iterations * dim, dtype=np.uint32) if trace_paths else None
-        flags = (L.VRT_TRACE_PATHS if trace_paths else 0) | (L.VRT_TRACE_LIVE_TRANSLUCENCY if live_translucency else 0)
+        flags = (L.VRT_TRACE_PATHS if trace_paths else 0) | (L.VRT_TRACE_LIVE_TRANSLUCENCY if live_translucency else 0) | \
+                (L.VRT_TRACE_ROUND_HOST if round_host else 0)
         L.check(L.lib().vrt_trace(self._h, n, _p(pos), _p(d), _DT[d.dtype], _p(isc), int(minimum_brightness), int(iterations), flags,
                                   _p(epos), _p(edir), _p(eit), _p(light), _p(path)))
         if trace_paths:
@@ -184,8 +200,13 @@ class TraceRaysCu:
         L.check(L.lib().vrt_trace(self._h, n, ptr(pos), ptr(d), dt, _p(isc), int(minimum_brightness), int(iterations), flags,
                                   ptr(epos), ptr(edir), ptr(eit), ptr(light), None))
 
+    @staticmethod
+    def cap_hit():
+        """1 / 0 / -1: did any ray of this thread's last host-buffer trace end at the iteration cap (vrt_trace_cap_hit)."""
+        return int(L.lib().vrt_trace_cap_hit())
+
     def trace_device(self, pos, d, scale_vec, minimum_brightness, iterations, epos=None, edir=None, eit=None, light=None,
-                     path=None, live_translucency=False, stream=None):
+                     path=None, live_translucency=False, stream=None, round_host=False):
         """torch CUDA tensors in/out, enqueued on `stream` (default: torch's current stream); does not synchronise."""
         import torch
         n = pos.numel() // self.dim
@@ -195,7 +216,8 @@ class TraceRaysCu:
         light = torch.empty(n, dtype=torch.int32, device=pos.device) if light is None else light
         isc = np.ascontiguousarray(scale_vec, dtype=np.float32)
         st = torch.cuda.current_stream(pos.device) if stream is None else stream
-        flags = (L.VRT_TRACE_PATHS if path is not None else 0) | (L.VRT_TRACE_LIVE_TRANSLUCENCY if live_translucency else 0)
+        flags = (L.VRT_TRACE_PATHS if path is not None else 0) | (L.VRT_TRACE_LIVE_TRANSLUCENCY if live_translucency else 0) | \
+                (L.VRT_TRACE_ROUND_HOST if round_host else 0)
         dt = L.VRT_I16 if d.dtype == torch.int16 else L.VRT_F32
         L.check(L.lib().vrt_trace_device(self._h, n, C.c_void_p(pos.data_ptr()), C.c_void_p(d.data_ptr()), dt, _p(isc),
                                          int(minimum_brightness), int(iterations), flags, C.c_void_p(epos.data_ptr()),
@@ -210,6 +232,43 @@ class TraceRaysCu:
         dt = L.VRT_I16 if d.dtype == torch.int16 else L.VRT_F32
         L.check(L.lib().vrt_normalise_rays_device(self._h, pos.numel() // self.dim, C.c_void_p(pos.data_ptr()), C.c_void_p(d.data_ptr()),
                                                   dt, C.byref(bad), C.c_void_p(st.cuda_stream)))
+
+
+class Comm:
+    """One process per GPU: NCCL communicator owned by libvrt_b200.so (vrt_comm_*).  `exchange(bytes_or_None) -> bytes` hands
+    rank 0's 128-byte unique id to every rank (e.g. torch.distributed.broadcast_object_list, MPI, a file)."""
+
+    def __init__(self, device, rank, world, exchange):
+        self._c = C.c_void_p()
+        uid = None
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            L.check(L.lib().vrt_comm_unique_id(buf))
+            uid = buf.raw
+        uid = exchange(uid)
+        self.rank, self.world, self.device = rank, world, device
+        L.check(L.lib().vrt_comm_create(C.byref(self._c), device, rank, world, C.c_char_p(uid)))
+
+    def broadcast_scene(self, scene, root=0):
+        """Replicates root's scene to every rank with in-place ncclBroadcasts of the staged buffers (vrt_scene_broadcast).
+        Returns (TraceRaysCu on this rank, seconds of the payload broadcasts on the device)."""
+        out = C.c_void_p()
+        secs = C.c_double(0.0)
+        L.check(L.lib().vrt_scene_broadcast(self._c, root, scene._h if scene is not None else None, C.byref(out), C.byref(secs)))
+        if scene is not None and self.rank == root:
+            return scene, secs.value
+        return TraceRaysCu(None, None, None, _handle=out), secs.value
+
+    def close(self):
+        if self._c:
+            L.lib().vrt_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def VrtErrorCompat(msg):

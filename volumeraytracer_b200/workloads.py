@@ -140,12 +140,16 @@ def ior_to_u32(ior_f32):
 # ---------------------------------------------------------------------------------------------------
 # rays
 
-def rays_parallel_x(ny, nz, lo, hi, x0=2.0, lo_z=None, hi_z=None):
-    """ny*nz parallel +x rays on a uniform grid over [lo,hi]^2 (C2, C3, C5), z fastest."""
+def rays_parallel_x(ny, nz, lo, hi, x0=2.0, lo_z=None, hi_z=None, rows=None):
+    """ny*nz parallel +x rays on a uniform grid over [lo,hi]^2 (C2, C3, C5), z fastest.  rows=(j0, j1) returns only the
+    y-rows j0 <= j < j1 of that grid (a contiguous index range of the batch: one rank's shard), with identical bits."""
     lo_z = lo if lo_z is None else lo_z
     hi_z = hi if hi_z is None else hi_z
     ys = lo + (hi - lo) * (np.arange(ny, dtype=np.float64) / max(ny - 1, 1))
     zs = lo_z + (hi_z - lo_z) * (np.arange(nz, dtype=np.float64) / max(nz - 1, 1))
+    if rows is not None:
+        ys = ys[rows[0]:rows[1]]
+        ny = ys.size
     pos = np.empty((ny, nz, 3), dtype=np.uint32)
     pos[..., 0] = to_fixed(x0)
     pos[..., 1] = to_fixed(ys)[:, None]

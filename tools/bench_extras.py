@@ -210,7 +210,7 @@ def reference_cuda(dev, c5_window=512, size=1024, ray_side=4096, iterations=2048
         tp = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d.reshape(-1)).to(dev)
         sc.normalise_rays_device(tp, td)
         out["config5_window"] = beside("config 5, centre %d^2 of the 4096^2 rays through the matching %dx%dx%d sub-volume, cap %d" % (
-            c5_window, c5_window, ior.shape[0], ior.shape[1], ior.shape[2], iterations), sc, tp.cpu().numpy().view(np.uint32).reshape(-1, 3),
+            c5_window, ior.shape[0], ior.shape[1], ior.shape[2], iterations), sc, tp.cpu().numpy().view(np.uint32).reshape(-1, 3),
             td.cpu().numpy().reshape(-1, 3), iterations)
         sc.close()
         del ior, tr, tp, td

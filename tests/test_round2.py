@@ -311,3 +311,76 @@ def test_normalise_accepts_rays_in_the_last_half_voxel(vrt, oracle, kind):
     pos2, d2 = S.random_rays(shape, 2000, seed=8, dir_kind="f32" if kind == "f32" else "i16")
     sc.trace_rays(pos2, d2, [1, 1, 1], 0, 100)
     sc.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# wavefront marcher (incoherent batches) and the device-side coherence probe
+
+@pytest.mark.parametrize("volk,dirk,live", [("f32", "f32", False), ("i16", "i16", True), ("f32", "i16", True), ("i16", "f32", False)])
+def test_wavefront_mode_is_bit_identical(vrt, oracle, volk, dirk, live):
+    """VRT_OPT_WAVE_LOG2: rays bucketed by brick inside one cooperative launch, marched brick by brick with CTA-wide compaction,
+    suspended and resumed across rounds -- every output bit equals the single-launch marcher's and the oracle's."""
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (44, 38, 50), 91, volk, absorb=live, keep_i16=(volk == "i16" and live))
+    pos, d = S.random_rays(ob, 70000, seed=13, dir_kind=dirk, scale=1.2)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x2222)
+    pos[:50] = np.uint32(0xFFF00000)                              # rays that start outside the volume
+    isc = [1.0, 1.2, 0.85]
+    minb = 0x40000000 if live else 0
+    want = oracle.trace(vol, ob, pos, d, isc, 700, translucency=trc if live else None, min_brightness=minb, round_mode=oracle.ROUND_DEVICE)
+    for k, margin, check, tail in ((3, 2, 16, 20), (4, 0, 5, 0), (3, 1, 64, 500), (5, 3, 16, 1000), (3, 8, 1, 20)):
+        t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, margin)
+        t.set_option(vrt.VRT_OPT_WAVE_CHECK, check); t.set_option(vrt.VRT_OPT_WAVE_TAIL_PERMILLE, tail)
+        got = t.trace_rays_cu(pos, d, isc, minb, 700, live_translucency=live)
+        _assert_same(got, want[:4], "wavefront k=%d margin=%d check=%d tail=%d %s/%s" % (k, margin, check, tail, volk, dirk))
+        assert t.get_option(vrt.VRT_INFO_WAVE_ROUNDS) >= 1
+    # the cap: every ray that is still inside after `iterations` steps reports `iterations`, and the flag says so
+    t.set_option(vrt.VRT_OPT_WAVE_LOG2, 3); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, 2); t.set_option(vrt.VRT_OPT_WAVE_CHECK, 16)
+    want5 = oracle.trace(vol, ob, pos, d, isc, 5, translucency=trc if live else None, min_brightness=minb, round_mode=oracle.ROUND_DEVICE)
+    got5 = t.trace_rays_cu(pos, d, isc, minb, 5, live_translucency=live)
+    _assert_same(got5, want5[:4], "wavefront cap")
+    assert t.cap_hit() == 1
+    t.close()
+
+
+def test_device_probe_picks_the_marcher_without_a_sync(vrt, oracle):
+    """vrt_trace_device on a large volume: a probe KERNEL looks at the device-resident rays and gates the single-launch and the
+    wavefront marcher; a shuffled batch runs the wavefront kernel (rounds > 0), a coherent bundle does not (rounds == 0); the
+    results are the same bits either way and equal the oracle's on a subsample."""
+    import torch
+    from volumeraytracer_b200 import workloads as W
+    size = 200                                                   # 198^3 x 16 B = 124 MB: does not fit the 96 MB the probe asks for
+    ior = W.ior_sines(size, base=1.3, amp=0.08, period=40.0)
+    tr = np.full(ior.shape, 0xFFFFFFFF, np.uint32)
+    sc = vrt.TraceRaysCu.from_ior(ior.shape, ior, tr)
+    dev = torch.device("cuda", 0)
+    n = 1 << 18
+    pos, d = W.rays_random(n, 4.0, size - 5.0, 0xABCDE)
+    tp = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tp, td)
+    out = [o.cpu().numpy() for o in sc.trace_device(tp, td, [1, 1, 1], 0, 600)]
+    assert sc.get_option(vrt.VRT_INFO_WAVE_ROUNDS) > 1, "the probe should have chosen the wavefront marcher for a shuffled batch"
+    sc.set_option(vrt.VRT_OPT_WAVE_LOG2, -1)
+    ref_out = [o.cpu().numpy() for o in sc.trace_device(tp, td, [1, 1, 1], 0, 600)]
+    for a, b in zip(out, ref_out):
+        assert EQ(a, b)
+    vol, trc = sc.download_volume()
+    sel = np.arange(0, n, 64)
+    p_h = tp.cpu().numpy().view(np.uint32).reshape(-1, 3)[sel]; d_h = td.cpu().numpy().reshape(-1, 3)[sel]
+    want = oracle.trace(vol, sc._output_sizes, p_h, d_h, [1, 1, 1], 600, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(out[0].view(np.uint32).reshape(-1, 3)[sel], want[0]) and EQ(out[1].reshape(-1, 3)[sel], want[1]) and EQ(out[2].view(np.uint32)[sel], want[2])
+    # a coherent bundle of the same size: the gate keeps the single-launch marcher
+    sc.set_option(vrt.VRT_OPT_WAVE_LOG2, 0)
+    pos2, d2 = W.rays_parallel_x(512, 512, 4.0, size - 5.0, x0=2.0)
+    tp2 = torch.from_numpy(pos2.view(np.int32).reshape(-1)).to(dev); td2 = torch.from_numpy(d2.reshape(-1)).to(dev)
+    sc.normalise_rays_device(tp2, td2)
+    out2 = [o.cpu().numpy() for o in sc.trace_device(tp2, td2, [1, 1, 1], 0, 600)]
+    assert sc.get_option(vrt.VRT_INFO_WAVE_ROUNDS) == 0
+    sel2 = np.arange(0, pos2.shape[0], 64)
+    p_h = tp2.cpu().numpy().view(np.uint32).reshape(-1, 3)[sel2]; d_h = td2.cpu().numpy().reshape(-1, 3)[sel2]
+    want2 = oracle.trace(vol, sc._output_sizes, p_h, d_h, [1, 1, 1], 600, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(out2[0].view(np.uint32).reshape(-1, 3)[sel2], want2[0]) and EQ(out2[2].view(np.uint32)[sel2], want2[2])
+    # and the host call makes the same choice with its host-side probe
+    got_h = sc.trace_rays_cu(tp.cpu().numpy().view(np.uint32).reshape(-1, 3), td.cpu().numpy().reshape(-1, 3), [1, 1, 1], 0, 600)
+    assert sc.get_option(vrt.VRT_INFO_WAVE_ROUNDS) > 1
+    assert EQ(got_h[0].reshape(-1), out[0].view(np.uint32)) and EQ(got_h[2], out[2].view(np.uint32))
+    sc.close()

@@ -28,12 +28,39 @@ def timed(fn, reps=2):
     return best, out
 
 
+KV_OPTS = {"wave": "VRT_OPT_WAVE_LOG2", "margin": "VRT_OPT_WAVE_MARGIN", "check": "VRT_OPT_WAVE_CHECK", "tail": "VRT_OPT_WAVE_TAIL_PERMILLE",
+           "wctas": "VRT_OPT_WAVE_CTAS_PER_SM", "region": "VRT_OPT_REGION_LOG2", "rounds": "VRT_OPT_REGION_ROUNDS", "kver": "VRT_OPT_KERNEL",
+           "block": "VRT_OPT_BLOCK_THREADS", "refill": "VRT_OPT_REFILL", "poll": "VRT_OPT_STEPS_PER_POLL", "ctas": "VRT_OPT_MAX_CTAS_PER_SM"}
+KV_DEFAULTS = {"wave": -1, "margin": 2, "check": 16, "tail": 20, "wctas": 0, "region": 0, "rounds": 12, "kver": 0, "block": 128, "refill": 32, "poll": 128, "ctas": 0}
+
+
+def run_kv_variants(name, co, tpos, tdir, iterations, variants, live=False):
+    """variants: dicts of option short names (KV_OPTS); unspecified options take KV_DEFAULTS"""
+    first = None
+    for var in variants:
+        opts = dict(KV_DEFAULTS); opts.update(var)
+        for k, v in opts.items():
+            co.set_option(getattr(vrt, KV_OPTS[k]), v)
+        t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
+        steps = int(out[2].to(torch.int64).sum().item())
+        same = None
+        if first is None:
+            first = [o.clone() for o in out]
+        else:
+            same = bool(all(torch.equal(a, b) for a, b in zip(out, first)))
+        rounds = co.get_option(vrt.VRT_INFO_WAVE_ROUNDS) if opts["wave"] >= 0 else None
+        print(json.dumps(dict(cfg=name, **var, sec=round(t, 4), steps=steps, grays=round(steps / t / 1e9, 2), same_bits_as_first=same, wave_rounds=rounds)), flush=True)
+
+
 def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
+    if variants and isinstance(variants[0], dict):
+        return run_kv_variants(name, co, tpos, tdir, iterations, variants, live)
     res = []
     for var in variants:
         kver, block, refill, poll = var[:4]
         ctas = var[4] if len(var) > 4 else 0
         region = var[5] if len(var) > 5 else 0
+        co.set_option(vrt.VRT_OPT_WAVE_LOG2, -1)
         co.set_option(vrt.VRT_OPT_REGION_LOG2, region)
         co.set_option(vrt.VRT_OPT_REGION_ROUNDS, var[6] if len(var) > 6 else 24)
         co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)
@@ -51,7 +78,10 @@ def _env_variants():
     v = os.environ.get("SWEEP_VARIANTS")
     if not v:
         return None
-    return [tuple(int(x) for x in item.split(",")) for item in v.replace(";", ":").split(":")]
+    items = v.replace(";", ":").split(":")
+    if "=" in v:            # key=value form: "wave=4,margin=2:wave=-1"
+        return [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in item.split(",") if kv) for item in items]
+    return [tuple(int(x) for x in item.split(",")) for item in items]
 
 
 VARIANTS = _env_variants() or [(1, 128, 0, 8), (2, 128, 0, 8), (3, 128, 0, 8), (3, 256, 0, 8), (3, 64, 0, 8), (3, 128, 32, 8), (3, 128, 16, 8),

@@ -14,6 +14,7 @@
 #include "vrt_march.cuh"
 #include "vrt_prep.cuh"
 #include "vrt_region.cuh"
+#include "vrt_wave.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -94,9 +95,20 @@ struct vrt_scene
     uint64_t  ior_bounds[3] = {1, 1, 1};
     bool      owns_ior = false;
     int       num_sms = 148;
+    mutable uint32_t *d_wave_info = nullptr; // [kCtlWords] copy of the wavefront marcher's control block after its last launch (rounds, ...)
+    int64_t last_wave_rounds_host() const
+    {
+        if (!d_wave_info) return 0;
+        uint32_t h[vrt::kCtlWords] = {};
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h, d_wave_info, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+        return (int64_t)h[vrt::kCtlRounds];
+    }
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: 8 block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{2}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -401,6 +413,7 @@ int vrt_scene_destroy(vrt_scene *s)
     if (s->owns) { cudaFree(s->d_volume); cudaFree(s->d_translucency); }
     if (s->owns_ior) cudaFree(s->d_ior);
     if (s->d_stats) cudaFree(s->d_stats);
+    if (s->d_wave_info) cudaFree(s->d_wave_info);
     cudaGetLastError();
     pool_release(s->device);
     delete s;
@@ -652,6 +665,11 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_MAX_CTAS_PER_SM: if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "max CTAs per SM must be 0..32"); s->opt_max_ctas = v; break;
     case VRT_OPT_REGION_LOG2:    if (v != 0 && v != -1 && (v < 5 || v > 9)) return fail(VRT_ERR_INVALID, "region log2 must be -1, 0 or 5..9"); s->opt_region = v; break;
     case VRT_OPT_REGION_ROUNDS:  if (v < 1 || v > 256) return fail(VRT_ERR_INVALID, "region rounds must be 1..256"); s->opt_rounds = v; break;
+    case VRT_OPT_WAVE_LOG2:      if (v != 0 && v != -1 && (v < 3 || v > 8)) return fail(VRT_ERR_INVALID, "wavefront brick log2 must be -1, 0 or 3..8"); s->opt_wave = v; break;
+    case VRT_OPT_WAVE_MARGIN:    if (v < 0 || v > 64) return fail(VRT_ERR_INVALID, "wavefront margin must be 0..64"); s->opt_wave_margin = v; break;
+    case VRT_OPT_WAVE_CHECK:     if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "wavefront steps per check must be 1..4096"); s->opt_wave_check = v; break;
+    case VRT_OPT_WAVE_TAIL_PERMILLE: if (v < 0 || v > 1000) return fail(VRT_ERR_INVALID, "wavefront tail must be 0..1000 permille"); s->opt_wave_tail = v; break;
+    case VRT_OPT_WAVE_CTAS_PER_SM: if (v < 0 || v > 8) return fail(VRT_ERR_INVALID, "wavefront CTAs per SM must be 0..8"); s->opt_wave_ctas = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -670,6 +688,12 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_MAX_CTAS_PER_SM: *v = s->opt_max_ctas; break;
     case VRT_OPT_REGION_LOG2: *v = s->opt_region; break;
     case VRT_OPT_REGION_ROUNDS: *v = s->opt_rounds; break;
+    case VRT_OPT_WAVE_LOG2: *v = s->opt_wave; break;
+    case VRT_OPT_WAVE_MARGIN: *v = s->opt_wave_margin; break;
+    case VRT_OPT_WAVE_CHECK: *v = s->opt_wave_check; break;
+    case VRT_OPT_WAVE_TAIL_PERMILLE: *v = s->opt_wave_tail; break;
+    case VRT_OPT_WAVE_CTAS_PER_SM: *v = s->opt_wave_ctas; break;
+    case VRT_INFO_WAVE_ROUNDS: *v = s->last_wave_rounds_host(); break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
     case VRT_INFO_STAT_BASE + 0: case VRT_INFO_STAT_BASE + 1: case VRT_INFO_STAT_BASE + 2: case VRT_INFO_STAT_BASE + 3:
@@ -706,6 +730,8 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     s->opt_kernel = src->opt_kernel.load(); s->opt_block = src->opt_block.load(); s->opt_refill = src->opt_refill.load();
     s->opt_chunk = src->opt_chunk.load(); s->opt_poll = src->opt_poll.load(); s->opt_max_ctas = src->opt_max_ctas.load();
     s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
+    s->opt_wave = src->opt_wave.load(); s->opt_wave_margin = src->opt_wave_margin.load(); s->opt_wave_check = src->opt_wave_check.load();
+    s->opt_wave_tail = src->opt_wave_tail.load(); s->opt_wave_ctas = src->opt_wave_ctas.load();
     *out = s;
     return VRT_OK;
 }
@@ -1181,6 +1207,84 @@ static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool
     return VRT_OK;
 }
 
+// ---- wavefront mode (vrt_wave.cuh): ONE cooperative launch does bucket passes + marching, round by round -------------------
+template <typename VoxT, bool DIR_I16, bool LIVE>
+static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
+{
+    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, 0);
+    if (e != cudaSuccess) return e;
+    const int cap = (int)s->opt_wave_ctas.load();
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    if (per_sm < 1) per_sm = 1;
+    const unsigned grid = (unsigned)(per_sm * s->num_sms);          // cooperative: every CTA must be resident
+    void *args[] = {(void *)&wp};
+    ++g_launches;
+    return cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kWaveThreads), args, 0, st);
+}
+
+static bool wave_geometry(const vrt_scene *s, int k, uint32_t nb[3], uint64_t *K)
+{
+    const uint64_t e = 1ull << k;
+    uint64_t tot = 1;
+    for (int d = 0; d < 3; ++d) { nb[d] = (uint32_t)((s->bounds[d] + e - 1) / e); tot *= nb[d]; }
+    *K = tot;
+    return tot < (1ull << 24);           // histogram / cursors / work items stay small next to the ray state
+}
+
+static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di16, bool live, cudaStream_t st, int k)
+{
+    const uint64_t n = mp.n;
+    uint32_t nb[3]; uint64_t K = 0;
+    if (!wave_geometry(s, k, nb, &K)) return fail(VRT_ERR_INVALID, "too many bricks: raise VRT_OPT_WAVE_LOG2");
+    if (n >= (1ull << 31)) return fail(VRT_ERR_INVALID, "wavefront mode takes at most 2^31-1 rays per call");
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device);
+    if (!coop) return fail(VRT_ERR_UNSUPPORTED, "device does not support cooperative launches");
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t max_items = (size_t)K + n / kWaveThreads + 2;
+    const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4), o_key = o_light + al(n * 4);
+    const size_t o_o0 = o_key + al(n * 4), o_o1 = o_o0 + al(n * 4), o_h0 = o_o1 + al(n * 4), o_h1 = o_h0 + al(K * 4), o_off = o_h1 + al(K * 4);
+    const size_t o_items = o_off + al((K + 1) * 4), o_part = o_items + al(max_items * 16), o_ctl = o_part + al(4096 * 8), total = o_ctl + 256;
+    char *ws = nullptr;
+    VRT_CUDA(pool_alloc((void **)&ws, total, s->device, st));
+    WaveParams wp;
+    wp.m = mp;
+    wp.m.counter = nullptr; wp.m.refill = 0;
+    wp.st_pos = (uint32_t *)(ws + o_pos); wp.st_dir = (float *)(ws + o_dir); wp.st_it = (uint32_t *)(ws + o_it); wp.st_light = (uint32_t *)(ws + o_light);
+    wp.key_of_ray = (uint32_t *)(ws + o_key);
+    wp.order[0] = (uint32_t *)(ws + o_o0); wp.order[1] = (uint32_t *)(ws + o_o1);
+    wp.hist[0] = (uint32_t *)(ws + o_h0); wp.hist[1] = (uint32_t *)(ws + o_h1);
+    wp.bin_off = (uint32_t *)(ws + o_off);
+    wp.items = (uint4 *)(ws + o_items);
+    wp.partial = (uint2 *)(ws + o_part);
+    wp.ctl = (uint32_t *)(ws + o_ctl);
+    wp.log2_brick = k; wp.margin = (uint32_t)s->opt_wave_margin.load();
+    wp.nby = nb[1]; wp.nbz = nb[2]; wp.K = (uint32_t)K;
+    wp.tail_rays = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(n * (uint64_t)s->opt_wave_tail.load() / 1000, 1024));
+    wp.steps_per_check = (int)s->opt_wave_check.load();
+    wp.max_rounds = mp.iterations + 8u < mp.iterations ? 0xFFFFFFFFu : mp.iterations + 8u;
+    cudaError_t err = cudaMemsetAsync(wp.ctl, 0, 256, st);
+    if (err == cudaSuccess)
+    {
+        if (s->store == VRT_F32)
+            err = di16 ? (live ? launch_wave<float, true, true>(s, wp, st) : launch_wave<float, true, false>(s, wp, st))
+                       : (live ? launch_wave<float, false, true>(s, wp, st) : launch_wave<float, false, false>(s, wp, st));
+        else
+            err = di16 ? (live ? launch_wave<int16_t, true, true>(s, wp, st) : launch_wave<int16_t, true, false>(s, wp, st))
+                       : (live ? launch_wave<int16_t, false, true>(s, wp, st) : launch_wave<int16_t, false, false>(s, wp, st));
+    }
+    if (err == cudaSuccess)
+    {
+        if (!s->d_wave_info && cudaMalloc((void **)&s->d_wave_info, kCtlWords * 4) != cudaSuccess) { cudaGetLastError(); s->d_wave_info = nullptr; }
+        if (s->d_wave_info) cudaMemcpyAsync(s->d_wave_info, wp.ctl, kCtlWords * 4, cudaMemcpyDeviceToDevice, st);
+    }
+    cudaFreeAsync(ws, st);
+    VRT_CUDA(err);
+    return VRT_OK;
+}
+
 static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const void *dir, int dir_dtype, const float *invscale,
                           uint32_t iterations, unsigned flags, const void *epos, const void *edir, const void *eit, const void *light, const void *path)
 {
@@ -1197,12 +1301,23 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     return VRT_OK;
 }
 
+// which marcher enqueue_march uses: the single launch (default), round 1's region mode (explicit request only), the wavefront
+// marcher, or -- gate != null -- whichever the device-side probe flag selects (gate_want: the flag value this launch runs for)
+struct MarchMode
+{
+    int region_log2 = 0;
+    int wave_log2 = 0;
+    const uint32_t *gate = nullptr;
+    uint32_t gate_want = 0;
+};
+
 // enqueue one marcher launch on `st`; `scratch` is a 16-byte device scratch (zeroed here: [0] = refill counter, [1] = cap flag,
 // read back by vrt_trace) or null for static mode without a cap flag
 static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void *d_dir, int dir_dtype, const float *invscale,
                          uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
-                         uint32_t *d_light, uint32_t *d_path, unsigned long long *scratch, cudaStream_t st, int region_log2)
+                         uint32_t *d_light, uint32_t *d_path, unsigned long long *scratch, cudaStream_t st, const MarchMode &mode)
 {
+    const int region_log2 = mode.region_log2;
     unsigned long long *counter = scratch && s->opt_refill.load() > 0 && s->dim == 3 ? scratch : nullptr;
     if (n == 0) return VRT_OK;
     MarchParams p;
@@ -1232,6 +1347,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
     p.cap_flag = scratch ? (uint32_t *)(scratch + 1) : nullptr;
+    p.mode_flag = mode.gate; p.mode_want = mode.gate_want;
     int kver = (int)s->opt_kernel.load();
     if (kver == 0) kver = 3;   // 6 (empty-space fast path) stays opt-in: it wins on coherent bundles through mostly empty volumes
                                // (config 1: 25x, config 2: +7 %) and loses where flat and curved cells mix inside a warp
@@ -1255,6 +1371,12 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     {
         if (s->bricked || s->tex || s->paired) return fail(VRT_ERR_UNSUPPORTED, "VRT_TRACE_ROUND_HOST needs the linear layout");
         kver = 8;
+    }
+    if (mode.wave_log2 > 0 && s->dim == 3 && !path && !s->tex && !s->bricked && !s->paired && !hostr)
+    {
+        // the gated pair shares one scratch: the single-launch marcher (enqueued first) has zeroed it; a stand-alone wavefront launch does it here
+        if (scratch && !mode.gate) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
+        return enqueue_march_wave(s, p, di16, live, st, mode.wave_log2);
     }
     if (region_log2 > 0 && s->dim == 3 && !path && !s->tex && !hostr)
     {
@@ -1339,10 +1461,17 @@ struct ThreadCtx
 static thread_local ThreadCtx t_ctx;
 static thread_local int t_cap_hit = -1;     // vrt_trace_cap_hit(): 1 / 0 / -1 (unknown)
 
-static uint64_t region_count(const vrt_scene *s, int k)
+// Is this batch a candidate for the wavefront marcher (the probe -- on the host for vrt_trace, on the device for vrt_trace_device --
+// then decides)?  Large 3-D batches over a volume that does not fit L2, linear layout, no path output, device rounding.  Returns the
+// brick log2 to use (4, or larger when the volume has too many 16^3 bricks), 0 = not a candidate.
+static int auto_wave_log2(const vrt_scene *s, uint64_t n, unsigned flags)
 {
-    const uint64_t e = 1ull << k;
-    return ((s->bounds[0] + e - 1) / e) * ((s->bounds[1] + e - 1) / e) * ((s->bounds[2] + e - 1) / e);
+    if (s->dim != 3 || (flags & (VRT_TRACE_PATHS | VRT_TRACE_ROUND_HOST)) || s->bricked || s->tex || s->paired) return 0;
+    if (n < (1u << 18) || n >= (1ull << 31)) return 0;
+    if (s->nvox * 4 * elem_size(s->store) <= (96ull << 20)) return 0;
+    uint32_t nb[3]; uint64_t K;
+    for (int k = 4; k <= 8; ++k) if (wave_geometry(s, k, nb, &K)) return k;
+    return 0;
 }
 
 extern "C" {
@@ -1356,12 +1485,33 @@ int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void
     DeviceGuard g(s->device);
     if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    unsigned long long *scratch = nullptr;
-    const bool refill = s->opt_refill.load() > 0 && s->dim == 3;
-    if (refill) VRT_CUDA(pool_alloc((void **)&scratch, 2 * sizeof(unsigned long long), s->device, st));
-    const int region = (int)std::max<int64_t>(0, s->opt_region.load());      // device buffers: region mode only on request
-    rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, scratch, st, region);
-    if (scratch) cudaFreeAsync(scratch, st);
+    unsigned long long *scratch = nullptr;       // [0] refill counter, [1] cap flag, [2] probe flag
+    VRT_CUDA(pool_alloc((void **)&scratch, 4 * sizeof(unsigned long long), s->device, st));
+    MarchMode mode;
+    mode.region_log2 = (int)std::max<int64_t>(0, s->opt_region.load());      // round 1's region mode: only on request
+    const int wave = mode.region_log2 > 0 ? -1 : (int)s->opt_wave.load();
+    if (wave > 0) mode.wave_log2 = wave;                                     // wavefront marcher on request
+    const int auto_k = wave == 0 ? auto_wave_log2(s, n, flags) : 0;
+    if (auto_k > 0)
+    {
+        // The batch lives in device memory and this call must not synchronise: a one-CTA probe kernel looks at the rays and writes a
+        // flag; the single-launch marcher and the wavefront marcher are BOTH enqueued, gated on that flag, and one of them returns
+        // at its first instruction.
+        uint32_t *flag = (uint32_t *)(scratch + 2);
+        coherence_probe_kernel<<<1, 256, 0, st>>>(d_pos, d_dir, dir_dtype == VRT_I16 ? 1 : 0, n, s->dim, flag);
+        ++g_launches;
+        VRT_CUDA(cudaGetLastError());
+        mode.gate = flag; mode.gate_want = 0;
+        rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, scratch, st, mode);
+        if (rc == VRT_OK)
+        {
+            mode.wave_log2 = auto_k; mode.gate_want = 1;
+            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, scratch, st, mode);
+        }
+    }
+    else
+        rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_epos, d_edir, d_eit, d_light, d_path, scratch, st, mode);
+    cudaFreeAsync(scratch, st);
     return rc;
 }
 
@@ -1377,17 +1527,21 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     const size_t ds = elem_size(dir_dtype);
     const bool want_path = flags & VRT_TRACE_PATHS;
     if (!t_ctx.ensure(s->device)) return fail(VRT_ERR_CUDA, "could not create the per-thread streams / staging buffers");
-    // region mode: on request (5..9), never (-1), or -- default 0 -- decided per batch by the host-side coherence probe
-    int region = (int)s->opt_region.load();
-    if (region == 0 && dim == 3 && !want_path && !s->bricked && !s->tex && n >= (1u << 18) &&
-        s->nvox * 4 * elem_size(s->store) > (96ull << 20) && batch_is_incoherent(n, dim, pos, dir, dir_dtype))
+    // Incoherent batches: round 1's region mode on explicit request (VRT_OPT_REGION_LOG2 5..9; thin, wide volumes whose region count
+    // does not fit its 16-bit key are refused there), the wavefront marcher on request (VRT_OPT_WAVE_LOG2 3..8) or -- default -- when the
+    // host-side coherence probe says that most neighbouring rays of the batch are not neighbours in space.
+    MarchMode mode;
+    mode.region_log2 = (int)std::max<int64_t>(0, s->opt_region.load());
     {
-        // automatic choice: the region key is 16 bits, so thin, wide volumes need larger regions -- or stay with the single launch
-        region = 6;
-        while (region <= 9 && region_count(s, region) >= kRegionDone) ++region;
-        if (region > 9) region = 0;
+        const int wave = mode.region_log2 > 0 ? -1 : (int)s->opt_wave.load();
+        if (wave > 0) mode.wave_log2 = wave;
+        else if (wave == 0)
+        {
+            const int k = auto_wave_log2(s, n, flags);
+            if (k > 0 && batch_is_incoherent(n, dim, pos, dir, dir_dtype)) mode.wave_log2 = k;
+        }
     }
-    if (region < 0) region = 0;
+    const int region = std::max(mode.region_log2, mode.wave_log2);      // either: fewer, larger chunks (below)
     t_cap_hit = -1;
 
     // Small batches (latency path): one packed H2D, one launch, one packed D2H through pinned staging -- 2 copies instead
@@ -1403,8 +1557,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             VRT_CUDA(cudaMemcpyAsync(d, h, b_pos + b_dir, cudaMemcpyHostToDevice, q));
             uint32_t *d_pos = (uint32_t *)d; void *d_dir = d + b_pos;
             uint32_t *d_eit = (uint32_t *)(d + b_pos + b_dir), *d_light = (uint32_t *)(d + b_pos + b_dir + b_u32);
-            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, nullptr, nullptr, q,
-                               (int)std::max<int64_t>(0, s->opt_region.load()));
+            rc = enqueue_march(s, n, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, d_eit, d_light, nullptr, nullptr, q, mode);
             if (rc) return rc;
             VRT_CUDA(cudaMemcpyAsync(h, d, b_pos + b_dir + 2 * b_u32, cudaMemcpyDeviceToHost, q));
             VRT_CUDA(cudaStreamSynchronize(q));
@@ -1502,7 +1655,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             uint32_t *d_pos = (uint32_t *)c.buf; void *d_dir = c.buf + c.o_dir;
             int rc2 = enqueue_march(s, m, d_pos, d_dir, dir_dtype, invscale, minb, iterations, flags, d_pos, d_dir, (uint32_t *)(c.buf + c.o_eit),
                                     (uint32_t *)(c.buf + c.o_light), want_path ? (uint32_t *)(c.buf + c.o_path) : nullptr,
-                                    (unsigned long long *)(c.buf + o_cnt), q, region);
+                                    (unsigned long long *)(c.buf + o_cnt), q, mode);
             if (rc2 && result == VRT_OK) result = rc2;
         }
         note(cudaEventRecord(c.marched, q));

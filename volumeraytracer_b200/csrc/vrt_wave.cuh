@@ -1,0 +1,382 @@
+// vrt_wave.cuh -- the marcher for INCOHERENT ray batches: one persistent cooperative kernel that re-orders the WORK, round by round.
+//
+// Randomly directed rays (BASELINE config 4) defeat the single-launch marcher twice over: its warps run nearly empty (rays end
+// after 2..4095 steps, a warp lives as long as its longest ray) and every cell change is a scattered fetch from a 2 GB volume
+// (75 B of DRAM traffic per ray-step).  Here the volume is cut into bricks of 2^k voxels per axis and the trace runs in rounds
+// inside ONE kernel launch (grid-wide barriers between the phases of a round, nothing returns to the host):
+//     1. bucket pass   counting sort of the rays still alive by the brick they are in: a histogram that the previous round's march
+//                      already filled, a grid-wide exclusive scan that also cuts every brick's ray list into work items of <= 256
+//                      rays, and a scatter of the ray ids (the sort need not be stable: results are written by ray id)
+//     2. march         a CTA takes a work item -- up to 256 rays that are all inside ONE brick -- and marches them until each has
+//                      left the brick (plus a margin that keeps rays from bouncing between two bricks) or has finished.  All
+//                      gathers of the CTA fall into one small box of the volume, so they are served by L1/L2, and every few steps
+//                      the CTA COMPACTS its live rays into the fewest warps (state through shared memory), so issue slots are not
+//                      spent on warps with one or two live lanes.  A ray that leaves the box writes its exact internal state
+//                      (fixed-point position, scaled float direction, step counter, brightness) back and is counted into the next
+//                      round's histogram.
+// When few rays are left (a brick then holds too few to fill a CTA) a last round marches the rest without a box.  Every step is
+// computed exactly like in march3_kernel (same operation order: cu:317-374), so results are bit-identical to the single launch.
+// This replaces round 1's region mode (13 cub radix sorts + 14 launches per trace).
+//
+// The kernel can be GATED by a device flag written by coherence_probe_kernel, so that vrt_trace_device -- which cannot look at
+// device buffers without a synchronisation -- enqueues probe + single-launch marcher + this kernel and exactly one of the two
+// marchers does the work.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "vrt_march.cuh"
+
+namespace vrt {
+
+namespace cg = cooperative_groups;
+
+#ifndef VRT_WAVE_MINCTAS
+#define VRT_WAVE_MINCTAS 3     // 3 x 256 threads per SM -> up to 85 registers: no spills (4 CTAs / 64 registers spills the corner cache)
+#endif
+
+constexpr uint32_t kWaveDone = 0xFFFFFFFFu;
+constexpr int      kWaveThreads = 256;           // threads per CTA = rays per work item
+constexpr uint32_t kItemUnboxed = 0x80000000u;   // work item flag: no box (last round)
+
+// control block (device): written by the scan phase, read by everybody after the grid barrier
+enum { kCtlAlive = 0, kCtlItems = 1, kCtlItemCursor = 2, kCtlTail = 3, kCtlPrevCount = 4, kCtlRounds = 5, kCtlWords = 8 };
+
+struct WaveParams
+{
+    MarchParams m;               // volume, limits, invscale, inputs, outputs, n, cap flag; mode_flag/mode_want gate the launch
+    uint32_t  *st_pos;           // [n][3] suspended position
+    float     *st_dir;           // [n][3] suspended internal direction (already scaled by 2^16 / 2^8)
+    uint32_t  *st_it;            // [n]    remaining-iterations counter (the reference's raydata_t::_iterations)
+    uint32_t  *st_light;         // [n]    brightness (live translucency only)
+    uint32_t  *key_of_ray;       // [n]    brick of the ray after the last round, kWaveDone when finished
+    uint32_t  *order[2];         // [n]    ray ids of the rays alive, grouped by brick (ping-pong)
+    uint32_t  *hist[2];          // [K]    rays per brick for this / the next round
+    uint32_t  *bin_off;          // [K+1]  scatter cursor of every brick (starts at the brick's offset into order[]); [K]: the tail round's single cursor
+    uint4     *items;            // work items: {brick | flags, first slot in order[], ray count, 0}
+    uint2     *partial;          // [gridDim] per-CTA (rays, items) of the scan
+    uint32_t  *ctl;              // [kCtlWords]
+    int        log2_brick;       // brick edge = 2^log2_brick voxels
+    uint32_t   margin;           // voxels a ray may travel beyond its brick before it is suspended
+    uint32_t   nby, nbz, K;      // bricks along axes 1, 2; number of bricks
+    uint32_t   tail_rays;        // when at most this many rays are alive the rest is marched without a box
+    int        steps_per_check;  // marching steps between two CTA-wide live counts / compactions
+    uint32_t   max_rounds;       // safety net (a round always advances every ray by at least one step)
+};
+
+__device__ __forceinline__ uint32_t wave_key(uint32_t px, uint32_t py, uint32_t pz, const WaveParams &p)
+{
+    // rays outside the volume get the key of the nearest brick: the march retires them on its first bounds test
+    const uint32_t ix = min(px >> 16, p.m.limx) >> p.log2_brick, iy = min(py >> 16, p.m.limy) >> p.log2_brick, iz = min(pz >> 16, p.m.limz) >> p.log2_brick;
+    return (ix * p.nby + iy) * p.nbz + iz;
+}
+
+// Device-side coherence probe (the host-side twin is batch_is_incoherent() in vrt_api.cu): are neighbouring rays of the batch
+// neighbours in space?  4096 scattered pairs (i, i+1); a pair is incoherent when its start positions are more than 4 voxels
+// apart or its directions differ by more than ~25 degrees.  *flag = 1 when most pairs are incoherent, else 0.  One CTA.
+__global__ void coherence_probe_kernel(const uint32_t *pos, const void *dir, int dir_i16, unsigned long long n, int dim, uint32_t *flag)
+{
+    __shared__ unsigned s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const unsigned long long samples = n < 2 ? 0 : (n - 1 < 4096 ? n - 1 : 4096);
+    unsigned bad = 0;
+    for (unsigned long long j = threadIdx.x; j < samples; j += blockDim.x)
+    {
+        const unsigned long long i = ((j * 0x9E3779B97F4A7C15ull) >> 11) % (n - 1);
+        bool far = false;
+        float dot = 0, na = 0, nb = 0;
+        for (int d = 0; d < dim; ++d)
+        {
+            const int32_t dp = (int32_t)(pos[(i + 1) * dim + d] - pos[i * dim + d]);
+            if (dp > (4 << 16) || dp < -(4 << 16)) far = true;
+            const float a = dir_i16 ? (float)((const short *)dir)[i * dim + d] : ((const float *)dir)[i * dim + d];
+            const float b = dir_i16 ? (float)((const short *)dir)[(i + 1) * dim + d] : ((const float *)dir)[(i + 1) * dim + d];
+            dot += a * b; na += a * a; nb += b * b;
+        }
+        if (far || !(dot * dot >= 0.81f * na * nb && dot >= 0)) ++bad;
+    }
+    if (bad) atomicAdd(&s_bad, bad);
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = (samples > 0 && s_bad * 2 > samples) ? 1u : 0u;
+}
+
+// block-wide exclusive scan of one (a, b) pair per thread; returns the block totals in (ta, tb)
+__device__ __forceinline__ void block_scan_pair(uint32_t &a, uint32_t &b, uint32_t &ta, uint32_t &tb, uint2 *s_warp /* [kWaveThreads / 32 + 1] */)
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, ia, o), xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        if (lane >= (unsigned)o) { ia += xa; ib += xb; }
+    }
+    if (lane == 31) s_warp[warp] = make_uint2(ia, ib);
+    __syncthreads();
+    uint32_t ba = 0, bb = 0, sa = 0, sb = 0;
+#pragma unroll
+    for (int w = 0; w < kWaveThreads / 32; ++w)
+    {
+        const uint2 v = s_warp[w];
+        if ((unsigned)w < warp) { ba += v.x; bb += v.y; }
+        sa += v.x; sb += v.y;
+    }
+    __syncthreads();
+    a = ba + ia - a; b = bb + ib - b;      // exclusive
+    ta = sa; tb = sb;
+}
+
+template <typename VoxT, bool DIR_I16, bool LIVE>
+__global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_kernel(const WaveParams p)
+{
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const MarchParams &m = p.m;
+    if (m.mode_flag != nullptr && *m.mode_flag != m.mode_want) return;       // gated launch: the probe chose the other marcher (uniform over the grid)
+    cg::grid_group grid = cg::this_grid();
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + tid, gsize = (unsigned long long)gridDim.x * blockDim.x;
+
+    __shared__ uint2    s_scan[kWaveThreads / 32 + 1];
+    __shared__ uint32_t s_live[2][kWaveThreads / 32];
+    __shared__ uint32_t s_xch[9][kWaveThreads];       // compaction: px py pz dx dy dz it brightness ray
+    __shared__ uint4    s_item;
+    __shared__ uint32_t s_base[2];
+
+    // ---- phase 0: every ray into the state arrays, first histogram ---------------------------------------------------------
+    for (unsigned long long i = gtid; i < (unsigned long long)p.K; i += gsize) { p.hist[0][i] = 0; p.hist[1][i] = 0; }
+    grid.sync();
+    for (unsigned long long i = gtid; i < m.n; i += gsize)
+    {
+        uint32_t px, py, pz; float dx, dy, dz;
+        load_ray<DIR_I16>(m, i, px, py, pz, dx, dy, dz);
+        p.st_pos[i * 3] = px; p.st_pos[i * 3 + 1] = py; p.st_pos[i * 3 + 2] = pz;
+        p.st_dir[i * 3] = dx; p.st_dir[i * 3 + 1] = dy; p.st_dir[i * 3 + 2] = dz;
+        p.st_it[i] = m.iterations - 1u;                                                          // cu:333
+        if (LIVE) p.st_light[i] = 0xFFFFFFFFu;                                                   // cu:332
+        const uint32_t key = wave_key(px, py, pz, p);
+        p.key_of_ray[i] = key;
+        atomicAdd(&p.hist[0][key], 1u);
+        p.order[1][i] = (uint32_t)i;                                                             // "previous list" of round 0: everybody
+    }
+    if (gtid == 0) { p.ctl[kCtlPrevCount] = (uint32_t)m.n; p.ctl[kCtlRounds] = 0; }
+    grid.sync();
+
+    int cur = 0;            // hist[cur] counts this round's rays; order[cur] is built from order[cur ^ 1]
+    for (uint32_t round = 0; round < p.max_rounds; ++round)
+    {
+        // ---- bucket pass 1a: per-CTA totals of (rays, work items) over the CTA's slice of bricks ------------------------------
+        const uint32_t slice = ((p.K + gridDim.x - 1) / gridDim.x + kWaveThreads - 1) / kWaveThreads * kWaveThreads;
+        const uint32_t b_lo = min(p.K, blockIdx.x * slice), b_hi = min(p.K, b_lo + slice);
+        {
+            uint32_t a = 0, b = 0, ta, tb;
+            for (uint32_t k = b_lo + tid; k < b_hi; k += kWaveThreads) { const uint32_t c = p.hist[cur][k]; a += c; b += (c + kWaveThreads - 1) / kWaveThreads; }
+            block_scan_pair(a, b, ta, tb, s_scan);
+            if (tid == 0) p.partial[blockIdx.x] = make_uint2(ta, tb);
+        }
+        grid.sync();
+        // ---- bucket pass 1b: offsets of the slice, work items, control block -----------------------------------------------------
+        {
+            uint32_t a = 0, b = 0, ta, tb;
+            for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint2 v = p.partial[c]; if (c < blockIdx.x) { a += v.x; b += v.y; } }
+            uint32_t ea = a, eb = b;
+            block_scan_pair(ea, eb, ta, tb, s_scan);                   // ta, tb = rays / items in the slices before this CTA's
+            if (tid == 0) { s_base[0] = ta; s_base[1] = tb; }
+            __syncthreads();
+            uint32_t off_r = s_base[0], off_i = s_base[1];
+            uint32_t alive = 0, nitems = 0;
+            if (blockIdx.x == 0)                                       // grand totals, by CTA 0
+            {
+                uint32_t x = 0, y = 0, tx, ty;
+                for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint2 v = p.partial[c]; x += v.x; y += v.y; }
+                block_scan_pair(x, y, tx, ty, s_scan);
+                alive = tx; nitems = ty;
+            }
+            for (uint32_t k0 = b_lo; k0 < b_hi; k0 += kWaveThreads)
+            {
+                const uint32_t k = k0 + tid;
+                const uint32_t c = k < b_hi ? p.hist[cur][k] : 0u;
+                uint32_t xr = c, xi = (c + kWaveThreads - 1) / kWaveThreads, tr_, ti_;
+                const uint32_t ni = xi;
+                block_scan_pair(xr, xi, tr_, ti_, s_scan);
+                if (k < b_hi)
+                {
+                    p.bin_off[k] = off_r + xr;
+                    for (uint32_t j = 0; j < ni; ++j)
+                        p.items[off_i + xi + j] = make_uint4(k, off_r + xr + j * kWaveThreads, min((uint32_t)kWaveThreads, c - j * kWaveThreads), 0u);
+                    p.hist[cur ^ 1][k] = 0;                            // the next round's histogram starts empty
+                }
+                off_r += tr_; off_i += ti_;
+            }
+            if (blockIdx.x == 0 && tid == 0)
+            {
+                p.bin_off[p.K] = 0;                                    // the tail round's single cursor
+                p.ctl[kCtlAlive] = alive; p.ctl[kCtlItems] = nitems; p.ctl[kCtlItemCursor] = 0;
+                p.ctl[kCtlTail] = alive <= p.tail_rays ? 1u : 0u;
+                p.ctl[kCtlRounds] = round + 1;
+            }
+        }
+        grid.sync();
+        const uint32_t alive = p.ctl[kCtlAlive], prev_count = p.ctl[kCtlPrevCount];
+        const bool tail = p.ctl[kCtlTail] != 0u;
+        if (alive == 0) break;                                                                   // uniform over the grid
+        // ---- bucket pass 2: scatter the ids of the rays still alive into their bricks' slots -------------------------------------
+        // (tail round: one list, in whatever order -- slot = a single global cursor, kept in bin_off[K])
+        for (unsigned long long i = gtid; i < prev_count; i += gsize)
+        {
+            const uint32_t ray = p.order[cur ^ 1][i];
+            const uint32_t k = p.key_of_ray[ray];
+            if (k != kWaveDone) p.order[cur][atomicAdd(&p.bin_off[tail ? p.K : k], 1u)] = ray;
+        }
+        grid.sync();
+        // ---- march -------------------------------------------------------------------------------------------------------------
+        const uint32_t nitems = tail ? (alive + kWaveThreads - 1) / kWaveThreads : p.ctl[kCtlItems];
+        for (;;)
+        {
+            if (tid == 0)
+            {
+                const uint32_t it_id = atomicAdd(&p.ctl[kCtlItemCursor], 1u);
+                uint4 w = make_uint4(0, 0, 0, 1u);                      // .w = 1: no more work
+                if (it_id < nitems)
+                    w = tail ? make_uint4(kItemUnboxed, it_id * kWaveThreads, min((uint32_t)kWaveThreads, alive - it_id * kWaveThreads), 0u) : p.items[it_id];
+                s_item = w;
+            }
+            __syncthreads();
+            const uint4 item = s_item;
+            __syncthreads();
+            if (item.w) break;
+
+            // the box this item's rays may march in during this round: [lo, lo + span) in 16.16, clipped to the volume
+            uint32_t lo_x = 0, lo_y = 0, lo_z = 0, sp_x = m.limx16, sp_y = m.limy16, sp_z = m.limz16;
+            if (!(item.x & kItemUnboxed))
+            {
+                const uint32_t e = 1u << p.log2_brick;
+                const uint32_t bz_ = item.x % p.nbz, by_ = (item.x / p.nbz) % p.nby, bx_ = item.x / (p.nbz * p.nby);
+                const uint32_t ax = bx_ * e, ay = by_ * e, az = bz_ * e;
+                const uint32_t l_x = ax > p.margin ? ax - p.margin : 0u, l_y = ay > p.margin ? ay - p.margin : 0u, l_z = az > p.margin ? az - p.margin : 0u;
+                const uint32_t h_x = min(ax + e + p.margin, m.limx), h_y = min(ay + e + p.margin, m.limy), h_z = min(az + e + p.margin, m.limz);
+                lo_x = l_x << 16; lo_y = l_y << 16; lo_z = l_z << 16;
+                sp_x = (h_x - l_x) << 16; sp_y = (h_y - l_y) << 16; sp_z = (h_z - l_z) << 16;
+            }
+            uint32_t px = 0, py = 0, pz = 0, it = 0, brightness = 0xFFFFFFFFu, cached_tr = 0, moved = 0xFFFFFFFFu, ray = 0;
+            float dx = 0, dy = 0, dz = 0;
+            bool have = tid < item.z;
+            if (have)
+            {
+                ray = p.order[cur][item.y + tid];
+                px = p.st_pos[(size_t)ray * 3]; py = p.st_pos[(size_t)ray * 3 + 1]; pz = p.st_pos[(size_t)ray * 3 + 2];
+                dx = p.st_dir[(size_t)ray * 3]; dy = p.st_dir[(size_t)ray * 3 + 1]; dz = p.st_dir[(size_t)ray * 3 + 2];
+                it = p.st_it[ray];
+                if (LIVE) brightness = p.st_light[ray];
+            }
+            CornersP q;
+            const float invx = m.invx, invy = m.invy, invz = m.invz;
+            for (uint32_t iter = 0;; ++iter)
+            {
+                if (have)
+                {
+                    const uint32_t it_stop = it - min(it, (uint32_t)p.steps_per_check);
+                    bool done = false, suspend = false;
+                    uint32_t it_final = 0;
+                    while (it != it_stop)
+                    {
+                        if (!(((px - lo_x) < sp_x) & ((py - lo_y) < sp_y) & ((pz - lo_z) < sp_z)))
+                        {
+                            // outside this round's box: either outside the volume (the reference's loop condition fails, cu:335) or only
+                            // outside the brick (suspend; the next round continues with exactly this state)
+                            if (!((px < m.limx16) & (py < m.limy16) & (pz < m.limz16))) { done = true; it_final = it; }
+                            else suspend = true;
+                            break;
+                        }
+                        --it;
+                        if (moved >= 0x10000u)
+                        {
+                            const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
+                            if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
+                            load_corners<VoxT>(q, m, cell);
+                        }
+                        if (LIVE)                                                                            // cu:337-341
+                        {
+                            const uint32_t absorb = 0xFFFFFFFFu - cached_tr;
+                            brightness -= min(brightness, absorb);
+                            if (brightness < m.min_brightness) { done = true; it_final = it + 1u; break; }
+                        }
+                        unsigned long long gxy, gzw;
+                        float gz, gw, sx, sy;
+                        trilerp_packed(q, px, py, pz, gxy, gzw, scale48_const());                            // cu:342
+                        unpack2(gzw, gz, gw);
+                        if (gw > 0.0f) { done = true; it_final = it + 1u; break; }                           // cu:343
+                        const unsigned long long dxy = fma2(pack2(invx, invy), gxy, pack2(dx, dy));          // cu:344-345
+                        dz = __fmaf_rn(invz, gz, dz);
+                        unpack2(dxy, dx, dy);
+                        const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                        const float ilen = div_is_fast(dot) ? div_fast(dot) : __fdiv_rn(0x42000000p0f, dot);  // cu:346 (div_fast is exact in its range)
+                        unpack2(mul2(mul2(pack2(invx, invy), dxy), pack2(ilen, ilen)), sx, sy);              // cu:347
+                        const uint32_t nx = px + (uint32_t)__float2int_rn(sx);
+                        const uint32_t ny = py + (uint32_t)__float2int_rn(sy);
+                        const uint32_t nz = pz + (uint32_t)__float2int_rn(__fmul_rn(__fmul_rn(invz, dz), ilen));
+                        moved = (px ^ nx) | (py ^ ny) | (pz ^ nz);
+                        px = nx; py = ny; pz = nz;
+                    }
+                    if (!done && !suspend && it == 0u) { done = true; it_final = 0u; }                       // cap (cu:335,350)
+                    if (done)
+                    {
+                        store_ray<DIR_I16, LIVE, false>(m, ray, px, py, pz, dx, dy, dz, it_final, brightness);
+                        p.key_of_ray[ray] = kWaveDone;
+                        have = false;
+                    }
+                    else if (suspend)
+                    {
+                        p.st_pos[(size_t)ray * 3] = px; p.st_pos[(size_t)ray * 3 + 1] = py; p.st_pos[(size_t)ray * 3 + 2] = pz;
+                        p.st_dir[(size_t)ray * 3] = dx; p.st_dir[(size_t)ray * 3 + 1] = dy; p.st_dir[(size_t)ray * 3 + 2] = dz;
+                        p.st_it[ray] = it;
+                        if (LIVE) p.st_light[ray] = brightness;
+                        const uint32_t key = wave_key(px, py, pz, p);
+                        p.key_of_ray[ray] = key;
+                        atomicAdd(&p.hist[cur ^ 1][key], 1u);
+                        have = false;
+                    }
+                }
+                // CTA-wide live count; compaction when it frees at least one warp
+                const unsigned live_mask = __ballot_sync(FULL, have);
+                const int par = iter & 1;
+                if (lane == 0) s_live[par][warp] = (uint32_t)__popc(live_mask);
+                __syncthreads();
+                uint32_t tot = 0, active = 0, before = 0;
+#pragma unroll
+                for (int w = 0; w < kWaveThreads / 32; ++w)
+                {
+                    const uint32_t c = s_live[par][w];
+                    tot += c; active += c ? 1u : 0u;
+                    if ((unsigned)w < warp) before += c;
+                }
+                if (tot == 0) break;                                                                         // uniform over the CTA
+                if (active > (tot + 31u) / 32u)
+                {
+                    if (have)
+                    {
+                        const uint32_t slot = before + (uint32_t)__popc(live_mask & ((1u << lane) - 1u));
+                        s_xch[0][slot] = px; s_xch[1][slot] = py; s_xch[2][slot] = pz;
+                        s_xch[3][slot] = __float_as_uint(dx); s_xch[4][slot] = __float_as_uint(dy); s_xch[5][slot] = __float_as_uint(dz);
+                        s_xch[6][slot] = it; s_xch[7][slot] = brightness; s_xch[8][slot] = ray;
+                    }
+                    __syncthreads();
+                    have = tid < tot;
+                    if (have)
+                    {
+                        px = s_xch[0][tid]; py = s_xch[1][tid]; pz = s_xch[2][tid];
+                        dx = __uint_as_float(s_xch[3][tid]); dy = __uint_as_float(s_xch[4][tid]); dz = __uint_as_float(s_xch[5][tid]);
+                        it = s_xch[6][tid]; brightness = s_xch[7][tid]; ray = s_xch[8][tid];
+                        moved = 0xFFFFFFFFu;                                                                 // the cached corners belong to another ray
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (gtid == 0) p.ctl[kCtlPrevCount] = alive;
+        grid.sync();
+        cur ^= 1;
+    }
+}
+
+} // namespace vrt

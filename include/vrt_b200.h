@@ -96,23 +96,22 @@ enum {
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
     VRT_OPT_CHUNK_RAYS    = 3,  /* vrt_trace (host buffers): rays per pipelined chunk, 0 = auto */
     VRT_OPT_STEPS_PER_POLL= 4,  /* marching steps between two refill polls */
-    VRT_OPT_REGION_LOG2   = 6,  /* round 1's region mode, kept for comparison, ONLY on request: the volume is cut into regions of 2^k voxels, rays
-                                   are sorted by region (cub radix sort) and marched region by region over several launches so that the gathers
-                                   are served by L2 instead of DRAM (bit-identical results; 3-D, no path output).  5..9: use it, with that k.
-                                   0 / -1 (default 0): not used -- incoherent batches go to the wavefront marcher, VRT_OPT_WAVE_LOG2 */
+    VRT_OPT_REGION_LOG2   = 6,  /* round 1's name for VRT_OPT_WAVE_LOG2 (its region mode -- a cub radix sort and a launch per round -- was replaced by
+                                   the wavefront marcher at the same marching rate); still accepted: 5..9 = wavefront marcher with that brick log2 */
     /* WAVEFRONT marcher for INCOHERENT batches (csrc/vrt_wave.cuh): one cooperative launch sorts the rays by 2^k-voxel brick with an
-       in-kernel counting sort, marches every brick's rays by one CTA until they leave the brick (CTA-wide compaction keeps the warps
-       full), and repeats until no ray is left; bit-identical results.  3..8: always, with that k.  -1: never.  0 (default): decided
+       in-kernel counting sort, marches them brick by brick -- persistent warps refilled from the sorted list, every ray until it leaves
+       its brick -- and repeats until no ray is left; bit-identical results.  3..8: always, with that k.  -1: never.  0 (default): decided
        per batch by a coherence probe of the ray buffers -- on the host for vrt_trace, by a probe KERNEL for vrt_trace_device (the
        single-launch and the wavefront marcher are then both enqueued, gated on the probe's flag; no synchronisation).  Only large
        3-D batches (>= 2^18 rays) over volumes that do not fit L2 are probed. */
     VRT_OPT_WAVE_LOG2     = 8,
-    VRT_OPT_WAVE_MARGIN   = 9,  /* voxels a ray may travel beyond its brick before it is re-bucketed (default 2) */
-    VRT_OPT_WAVE_CHECK    = 10, /* marching steps between two CTA-wide live counts / compactions (default 16) */
+    VRT_OPT_WAVE_MARGIN   = 9,  /* voxels a ray may travel beyond its brick before it is re-bucketed (default 8) */
+    VRT_OPT_WAVE_CHECK    = 10, /* marching steps between two refill polls of a warp (default 32) */
     VRT_OPT_WAVE_TAIL_PERMILLE = 11, /* when at most this share of the batch is still alive, the rest is marched without bricks (default 20) */
     VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = occupancy limit) */
+    VRT_OPT_WAVE_REFILL   = 14, /* a warp takes new rays from the brick-sorted list when at least this many lanes are idle (default 8) */
     VRT_INFO_WAVE_ROUNDS  = 102, /* read-only: rounds the last wavefront launch on this scene took (synchronises) */
-    VRT_OPT_REGION_ROUNDS = 7,  /* region mode: number of region-limited rounds before the final unrestricted one (default 12) */
+    VRT_OPT_REGION_ROUNDS = 7,  /* accepted for compatibility, unused (the wavefront marcher runs as many rounds as the batch needs) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
     VRT_INFO_NUM_SMS      = 101, /* read-only: multiprocessor count of the scene's device (cudaGetDeviceProperties) */

@@ -29,9 +29,9 @@ def timed(fn, reps=2):
 
 
 KV_OPTS = {"wave": "VRT_OPT_WAVE_LOG2", "margin": "VRT_OPT_WAVE_MARGIN", "check": "VRT_OPT_WAVE_CHECK", "tail": "VRT_OPT_WAVE_TAIL_PERMILLE",
-           "wctas": "VRT_OPT_WAVE_CTAS_PER_SM", "region": "VRT_OPT_REGION_LOG2", "rounds": "VRT_OPT_REGION_ROUNDS", "kver": "VRT_OPT_KERNEL",
+           "wctas": "VRT_OPT_WAVE_CTAS_PER_SM", "wrefill": "VRT_OPT_WAVE_REFILL", "region": "VRT_OPT_REGION_LOG2", "rounds": "VRT_OPT_REGION_ROUNDS", "kver": "VRT_OPT_KERNEL",
            "block": "VRT_OPT_BLOCK_THREADS", "refill": "VRT_OPT_REFILL", "poll": "VRT_OPT_STEPS_PER_POLL", "ctas": "VRT_OPT_MAX_CTAS_PER_SM"}
-KV_DEFAULTS = {"wave": -1, "margin": 2, "check": 16, "tail": 20, "wctas": 0, "region": 0, "rounds": 12, "kver": 0, "block": 128, "refill": 32, "poll": 128, "ctas": 0}
+KV_DEFAULTS = {"wave": -1, "margin": 8, "check": 32, "tail": 20, "wctas": 0, "wrefill": 8, "region": 0, "rounds": 12, "kver": 0, "block": 128, "refill": 32, "poll": 128, "ctas": 0}
 
 
 def run_kv_variants(name, co, tpos, tdir, iterations, variants, live=False):
@@ -39,6 +39,8 @@ def run_kv_variants(name, co, tpos, tdir, iterations, variants, live=False):
     first = None
     for var in variants:
         opts = dict(KV_DEFAULTS); opts.update(var)
+        if opts["region"] > 0 and "wave" not in var:
+            opts["wave"] = 0                      # VRT_OPT_REGION_LOG2 is an alias that only counts while VRT_OPT_WAVE_LOG2 is 0
         for k, v in opts.items():
             co.set_option(getattr(vrt, KV_OPTS[k]), v)
         t, out = timed(lambda: co.trace_device(tpos, tdir, [1, 1, 1], 0x40000000 if live else 0, iterations, live_translucency=live))
@@ -60,7 +62,7 @@ def run_variants(name, co, tpos, tdir, iterations, variants, live=False):
         kver, block, refill, poll = var[:4]
         ctas = var[4] if len(var) > 4 else 0
         region = var[5] if len(var) > 5 else 0
-        co.set_option(vrt.VRT_OPT_WAVE_LOG2, -1)
+        co.set_option(vrt.VRT_OPT_WAVE_LOG2, 0 if region > 0 else -1)
         co.set_option(vrt.VRT_OPT_REGION_LOG2, region)
         co.set_option(vrt.VRT_OPT_REGION_ROUNDS, var[6] if len(var) > 6 else 24)
         co.set_option(vrt.VRT_OPT_KERNEL, kver); co.set_option(vrt.VRT_OPT_BLOCK_THREADS, block)

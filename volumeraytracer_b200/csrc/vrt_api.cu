@@ -13,10 +13,7 @@
 #include "../../include/vrt_b200.h"
 #include "vrt_march.cuh"
 #include "vrt_prep.cuh"
-#include "vrt_region.cuh"
 #include "vrt_wave.cuh"
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include <dlfcn.h>
 
@@ -108,7 +105,7 @@ struct vrt_scene
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: 8 block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
-    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{2}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{32}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -664,12 +661,13 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_STEPS_PER_POLL: if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "steps per poll must be 1..4096"); s->opt_poll = v; break;
     case VRT_OPT_MAX_CTAS_PER_SM: if (v < 0 || v > 32) return fail(VRT_ERR_INVALID, "max CTAs per SM must be 0..32"); s->opt_max_ctas = v; break;
     case VRT_OPT_REGION_LOG2:    if (v != 0 && v != -1 && (v < 5 || v > 9)) return fail(VRT_ERR_INVALID, "region log2 must be -1, 0 or 5..9"); s->opt_region = v; break;
-    case VRT_OPT_REGION_ROUNDS:  if (v < 1 || v > 256) return fail(VRT_ERR_INVALID, "region rounds must be 1..256"); s->opt_rounds = v; break;
+    case VRT_OPT_REGION_ROUNDS:  if (v < 1 || v > 256) return fail(VRT_ERR_INVALID, "region rounds must be 1..256"); s->opt_rounds = v; break;   // accepted, unused
     case VRT_OPT_WAVE_LOG2:      if (v != 0 && v != -1 && (v < 3 || v > 8)) return fail(VRT_ERR_INVALID, "wavefront brick log2 must be -1, 0 or 3..8"); s->opt_wave = v; break;
     case VRT_OPT_WAVE_MARGIN:    if (v < 0 || v > 64) return fail(VRT_ERR_INVALID, "wavefront margin must be 0..64"); s->opt_wave_margin = v; break;
     case VRT_OPT_WAVE_CHECK:     if (v < 1 || v > 4096) return fail(VRT_ERR_INVALID, "wavefront steps per check must be 1..4096"); s->opt_wave_check = v; break;
     case VRT_OPT_WAVE_TAIL_PERMILLE: if (v < 0 || v > 1000) return fail(VRT_ERR_INVALID, "wavefront tail must be 0..1000 permille"); s->opt_wave_tail = v; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: if (v < 0 || v > 8) return fail(VRT_ERR_INVALID, "wavefront CTAs per SM must be 0..8"); s->opt_wave_ctas = v; break;
+    case VRT_OPT_WAVE_REFILL:    if (v < 1 || v > 32) return fail(VRT_ERR_INVALID, "wavefront refill threshold must be 1..32"); s->opt_wave_refill = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -693,6 +691,7 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_WAVE_CHECK: *v = s->opt_wave_check; break;
     case VRT_OPT_WAVE_TAIL_PERMILLE: *v = s->opt_wave_tail; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: *v = s->opt_wave_ctas; break;
+    case VRT_OPT_WAVE_REFILL: *v = s->opt_wave_refill; break;
     case VRT_INFO_WAVE_ROUNDS: *v = s->last_wave_rounds_host(); break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
@@ -732,6 +731,7 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
     s->opt_wave = src->opt_wave.load(); s->opt_wave_margin = src->opt_wave_margin.load(); s->opt_wave_check = src->opt_wave_check.load();
     s->opt_wave_tail = src->opt_wave_tail.load(); s->opt_wave_ctas = src->opt_wave_ctas.load();
+    s->opt_wave_refill = src->opt_wave_refill.load();
     *out = s;
     return VRT_OK;
 }
@@ -1132,86 +1132,14 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
     return live ? launch2_k<VoxT, false, true>(p, path, hostr, block, st) : launch2_k<VoxT, false, false>(p, path, hostr, block, st);
 }
 
-// ---- region mode (vrt_region.cuh): sort by region, march region by region, all on the caller's stream ---------------
-template <typename VoxT, bool DIR_I16, bool LIVE>
-static cudaError_t launch_region(const vrt_scene *s, const RegionParams &rp, cudaStream_t st)
-{
-    auto kern = march3_region_kernel<VoxT, DIR_I16, LIVE>;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
-    if (e != cudaSuccess) return e;
-    const int cap = (int)s->opt_max_ctas.load();
-    if (cap > 0 && cap < per_sm) per_sm = cap;
-    if (per_sm < 1) per_sm = 1;
-    const unsigned long long want = (rp.m.n + 127) / 128;
-    const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)per_sm * s->num_sms, want);
-    kern<<<grid, 128, 0, st>>>(rp);
-    ++g_launches;
-    return cudaGetLastError();
-}
-
-static int enqueue_march_regions(const vrt_scene *s, const MarchParams &mp, bool di16, bool live, cudaStream_t st, int k)
-{
-    const uint64_t n = mp.n;
-    const uint32_t e = 1u << k;
-    const uint32_t rx = (uint32_t)((s->bounds[0] + e - 1) / e), ry = (uint32_t)((s->bounds[1] + e - 1) / e), rz = (uint32_t)((s->bounds[2] + e - 1) / e);
-    if ((uint64_t)rx * ry * rz >= kRegionDone) return fail(VRT_ERR_INVALID, "too many regions: raise VRT_OPT_REGION_LOG2");
-    if (n >= (1ull << 31)) return fail(VRT_ERR_INVALID, "region mode takes at most 2^31-1 rays per call (cub item count is int)");
-
-    // workspace: suspended ray state, two key/order buffers for the sort, cub scratch, the refill counter
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (int)n, 0, 16, st);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4);
-    const size_t o_k0 = o_light + al(n * 4), o_k1 = o_k0 + al(n * 2), o_o0 = o_k1 + al(n * 2), o_o1 = o_o0 + al(n * 4);
-    const size_t o_cnt = o_o1 + al(n * 4), o_cub = o_cnt + 256, total = o_cub + al(cub_bytes);
-    char *ws = nullptr;
-    VRT_CUDA(pool_alloc((void **)&ws, total, s->device, st));
-    RegionParams rp;
-    rp.m = mp;
-    rp.m.counter = (unsigned long long *)(ws + o_cnt);
-    // region rounds end ragged (rays suspend at different steps): refill early and poll often, unlike the single-launch marcher
-    rp.m.refill = std::min(8, std::max(1, (int)s->opt_refill.load()));
-    rp.m.steps_per_poll = std::min(32, mp.steps_per_poll);
-    rp.st_pos = (uint32_t *)(ws + o_pos); rp.st_dir = (float *)(ws + o_dir); rp.st_it = (uint32_t *)(ws + o_it); rp.st_light = (uint32_t *)(ws + o_light);
-    rp.log2_edge = k; rp.margin = std::min<uint32_t>(8u, e / 4); rp.ry = ry; rp.rz = rz;
-    uint16_t *keys[2] = {(uint16_t *)(ws + o_k0), (uint16_t *)(ws + o_k1)};
-    uint32_t *order[2] = {(uint32_t *)(ws + o_o0), (uint32_t *)(ws + o_o1)};
-    int cur = 0;
-    rp.keys = keys[cur]; rp.order = order[cur];
-    const unsigned ib = (unsigned)((n + 255) / 256);
-    if (di16) region_init_kernel<true><<<ib, 256, 0, st>>>(rp, order[cur]);
-    else      region_init_kernel<false><<<ib, 256, 0, st>>>(rp, order[cur]);
-    ++g_launches;
-    cudaError_t err = cudaGetLastError();
-    const int rounds = (int)s->opt_rounds.load();
-    for (int r = 0; r <= rounds && err == cudaSuccess; ++r)
-    {
-        err = cub::DeviceRadixSort::SortPairs(ws + o_cub, cub_bytes, keys[cur], keys[cur ^ 1], order[cur], order[cur ^ 1], (int)n, 0, 16, st);
-        cur ^= 1;
-        g_launches += 1;
-        rp.keys = keys[cur]; rp.order = order[cur];
-        rp.log2_edge = r < rounds ? k : -1;                       // the last round has no region limit: whatever is left runs to its end
-        if (err == cudaSuccess) err = cudaMemsetAsync(rp.m.counter, 0, sizeof(unsigned long long), st);
-        if (err != cudaSuccess) break;
-        if (s->store == VRT_F32)
-            err = di16 ? (live ? launch_region<float, true, true>(s, rp, st) : launch_region<float, true, false>(s, rp, st))
-                       : (live ? launch_region<float, false, true>(s, rp, st) : launch_region<float, false, false>(s, rp, st));
-        else
-            err = di16 ? (live ? launch_region<int16_t, true, true>(s, rp, st) : launch_region<int16_t, true, false>(s, rp, st))
-                       : (live ? launch_region<int16_t, false, true>(s, rp, st) : launch_region<int16_t, false, false>(s, rp, st));
-    }
-    cudaFreeAsync(ws, st);
-    VRT_CUDA(err);
-    return VRT_OK;
-}
-
 // ---- wavefront mode (vrt_wave.cuh): ONE cooperative launch does bucket passes + marching, round by round -------------------
 template <typename VoxT, bool DIR_I16, bool LIVE>
 static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
 {
     auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE>;
+    static std::atomic<unsigned long long> carved{0};  // per device: next to no shared memory in use, give the unified array to L1
+    const unsigned long long bit = 1ull << (s->device & 63);
+    if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, 0);
     if (e != cudaSuccess) return e;
@@ -1243,10 +1171,9 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device);
     if (!coop) return fail(VRT_ERR_UNSUPPORTED, "device does not support cooperative launches");
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t max_items = (size_t)K + n / kWaveThreads + 2;
     const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4), o_key = o_light + al(n * 4);
     const size_t o_o0 = o_key + al(n * 4), o_o1 = o_o0 + al(n * 4), o_h0 = o_o1 + al(n * 4), o_h1 = o_h0 + al(K * 4), o_off = o_h1 + al(K * 4);
-    const size_t o_items = o_off + al((K + 1) * 4), o_part = o_items + al(max_items * 16), o_ctl = o_part + al(4096 * 8), total = o_ctl + 256;
+    const size_t o_part = o_off + al((K + 1) * 4), o_ctl = o_part + al(4096 * 4), total = o_ctl + 256;
     char *ws = nullptr;
     VRT_CUDA(pool_alloc((void **)&ws, total, s->device, st));
     WaveParams wp;
@@ -1257,13 +1184,13 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
     wp.order[0] = (uint32_t *)(ws + o_o0); wp.order[1] = (uint32_t *)(ws + o_o1);
     wp.hist[0] = (uint32_t *)(ws + o_h0); wp.hist[1] = (uint32_t *)(ws + o_h1);
     wp.bin_off = (uint32_t *)(ws + o_off);
-    wp.items = (uint4 *)(ws + o_items);
-    wp.partial = (uint2 *)(ws + o_part);
+    wp.partial = (uint32_t *)(ws + o_part);
     wp.ctl = (uint32_t *)(ws + o_ctl);
     wp.log2_brick = k; wp.margin = (uint32_t)s->opt_wave_margin.load();
     wp.nby = nb[1]; wp.nbz = nb[2]; wp.K = (uint32_t)K;
     wp.tail_rays = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(n * (uint64_t)s->opt_wave_tail.load() / 1000, 1024));
     wp.steps_per_check = (int)s->opt_wave_check.load();
+    wp.refill = (uint32_t)s->opt_wave_refill.load();
     wp.max_rounds = mp.iterations + 8u < mp.iterations ? 0xFFFFFFFFu : mp.iterations + 8u;
     cudaError_t err = cudaMemsetAsync(wp.ctl, 0, 256, st);
     if (err == cudaSuccess)
@@ -1301,11 +1228,10 @@ static int validate_trace(const vrt_scene *s, uint64_t n, const void *pos, const
     return VRT_OK;
 }
 
-// which marcher enqueue_march uses: the single launch (default), round 1's region mode (explicit request only), the wavefront
-// marcher, or -- gate != null -- whichever the device-side probe flag selects (gate_want: the flag value this launch runs for)
+// which marcher enqueue_march uses: the single launch (default), the wavefront marcher, or -- gate != null -- whichever the
+// device-side probe flag selects (gate_want: the flag value this launch runs for)
 struct MarchMode
 {
-    int region_log2 = 0;
     int wave_log2 = 0;
     const uint32_t *gate = nullptr;
     uint32_t gate_want = 0;
@@ -1317,7 +1243,6 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
                          uint32_t minb, uint32_t iterations, unsigned flags, uint32_t *d_epos, void *d_edir, uint32_t *d_eit,
                          uint32_t *d_light, uint32_t *d_path, unsigned long long *scratch, cudaStream_t st, const MarchMode &mode)
 {
-    const int region_log2 = mode.region_log2;
     unsigned long long *counter = scratch && s->opt_refill.load() > 0 && s->dim == 3 ? scratch : nullptr;
     if (n == 0) return VRT_OK;
     MarchParams p;
@@ -1376,14 +1301,8 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     {
         // the gated pair shares one scratch: the single-launch marcher (enqueued first) has zeroed it; a stand-alone wavefront launch does it here
         if (scratch && !mode.gate) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
-        return enqueue_march_wave(s, p, di16, live, st, mode.wave_log2);
+        return enqueue_march_wave(s, p, di16, live, st, mode.wave_log2);       // in-place calls are fine: phase 0 has read every start buffer before the first result is written
     }
-    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex && !hostr)
-    {
-        if (scratch) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
-    }
-    if (region_log2 > 0 && s->dim == 3 && !path && !s->tex && !hostr)
-        return enqueue_march_regions(s, p, di16, live, st, region_log2);       // in-place calls are fine: the init pass has read every start buffer before the first result is written
     if (scratch) VRT_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), st));
     cudaError_t e = s->store == VRT_F32 ? launch_vox<float>(s, p, di16, live, path, kver, block, st)
                                         : launch_vox<int16_t>(s, p, di16, live, path, kver, block, st);
@@ -1394,7 +1313,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
 // Host-side coherence probe for vrt_trace: are neighbouring rays of the batch neighbours in space?  Samples up to 4096 pairs
 // (i, i+1): a pair is incoherent when its start positions are more than 4 voxels apart or its directions differ by more than
 // ~25 degrees.  Coherent bundles (a camera, a parallel beam) keep the single-launch marcher; mostly incoherent batches over a
-// volume that does not fit L2 are marched in region mode (same results, DRAM traffic replaced by L2 hits).
+// volume that does not fit L2 go to the wavefront marcher (same results, DRAM traffic replaced by L2 hits).
 static bool batch_is_incoherent(uint64_t n, int dim, const uint32_t *pos, const void *dir, int dir_dtype)
 {
     if (n < 2) return false;
@@ -1463,14 +1382,21 @@ static thread_local int t_cap_hit = -1;     // vrt_trace_cap_hit(): 1 / 0 / -1 (
 
 // Is this batch a candidate for the wavefront marcher (the probe -- on the host for vrt_trace, on the device for vrt_trace_device --
 // then decides)?  Large 3-D batches over a volume that does not fit L2, linear layout, no path output, device rounding.  Returns the
-// brick log2 to use (4, or larger when the volume has too many 16^3 bricks), 0 = not a candidate.
+// brick log2 to use (5: 32^3-voxel bricks, the fastest on config 4; larger when the volume has too many of them), 0 = not a candidate.
+// VRT_OPT_WAVE_LOG2 (and its round-1 alias VRT_OPT_REGION_LOG2: both name the brick edge): > 0 forced, 0 automatic, < 0 never
+static int wave_request(const vrt_scene *s)
+{
+    const int w = (int)s->opt_wave.load(), r = (int)s->opt_region.load();
+    return w != 0 ? w : r;
+}
+
 static int auto_wave_log2(const vrt_scene *s, uint64_t n, unsigned flags)
 {
     if (s->dim != 3 || (flags & (VRT_TRACE_PATHS | VRT_TRACE_ROUND_HOST)) || s->bricked || s->tex || s->paired) return 0;
     if (n < (1u << 18) || n >= (1ull << 31)) return 0;
     if (s->nvox * 4 * elem_size(s->store) <= (96ull << 20)) return 0;
     uint32_t nb[3]; uint64_t K;
-    for (int k = 4; k <= 8; ++k) if (wave_geometry(s, k, nb, &K)) return k;
+    for (int k = 5; k <= 8; ++k) if (wave_geometry(s, k, nb, &K)) return k;
     return 0;
 }
 
@@ -1488,8 +1414,7 @@ int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void
     unsigned long long *scratch = nullptr;       // [0] refill counter, [1] cap flag, [2] probe flag
     VRT_CUDA(pool_alloc((void **)&scratch, 4 * sizeof(unsigned long long), s->device, st));
     MarchMode mode;
-    mode.region_log2 = (int)std::max<int64_t>(0, s->opt_region.load());      // round 1's region mode: only on request
-    const int wave = mode.region_log2 > 0 ? -1 : (int)s->opt_wave.load();
+    const int wave = wave_request(s);
     if (wave > 0) mode.wave_log2 = wave;                                     // wavefront marcher on request
     const int auto_k = wave == 0 ? auto_wave_log2(s, n, flags) : 0;
     if (auto_k > 0)
@@ -1527,13 +1452,11 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     const size_t ds = elem_size(dir_dtype);
     const bool want_path = flags & VRT_TRACE_PATHS;
     if (!t_ctx.ensure(s->device)) return fail(VRT_ERR_CUDA, "could not create the per-thread streams / staging buffers");
-    // Incoherent batches: round 1's region mode on explicit request (VRT_OPT_REGION_LOG2 5..9; thin, wide volumes whose region count
-    // does not fit its 16-bit key are refused there), the wavefront marcher on request (VRT_OPT_WAVE_LOG2 3..8) or -- default -- when the
-    // host-side coherence probe says that most neighbouring rays of the batch are not neighbours in space.
+    // Incoherent batches: the wavefront marcher on request (VRT_OPT_WAVE_LOG2 3..8) or -- default -- when the host-side coherence probe
+    // says that most neighbouring rays of the batch are not neighbours in space.
     MarchMode mode;
-    mode.region_log2 = (int)std::max<int64_t>(0, s->opt_region.load());
     {
-        const int wave = mode.region_log2 > 0 ? -1 : (int)s->opt_wave.load();
+        const int wave = wave_request(s);
         if (wave > 0) mode.wave_log2 = wave;
         else if (wave == 0)
         {
@@ -1541,7 +1464,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             if (k > 0 && batch_is_incoherent(n, dim, pos, dir, dir_dtype)) mode.wave_log2 = k;
         }
     }
-    const int region = std::max(mode.region_log2, mode.wave_log2);      // either: fewer, larger chunks (below)
+    const int region = mode.wave_log2;                                  // wavefront mode: fewer, larger chunks (below)
     t_cap_hit = -1;
 
     // Small batches (latency path): one packed H2D, one launch, one packed D2H through pinned staging -- 2 copies instead
@@ -1577,7 +1500,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     // at least 2^17 rays per chunk (one wave of the persistent grid), at most 16 chunks: config 2 (1 M rays) through pageable buffers
     // runs 8 chunks at 224 G ray-steps/s instead of 2 chunks at 190
     if (chunk == 0) chunk = n <= (1u << 17) ? n : std::max<uint64_t>(1u << 17, (n + 15) / 16);
-    if (region > 0 && s->opt_chunk.load() == 0) chunk = std::max<uint64_t>(chunk, std::min<uint64_t>(n, 4u << 20));   // regions want many rays per sort
+    if (region > 0 && s->opt_chunk.load() == 0) chunk = std::max<uint64_t>(chunk, std::min<uint64_t>(n, 4u << 20));   // the wavefront marcher wants many rays per brick
     if (want_path)
     {
         const uint64_t per_ray = (uint64_t)iterations * dim * 4;

@@ -1,22 +1,26 @@
 // vrt_wave.cuh -- the marcher for INCOHERENT ray batches: one persistent cooperative kernel that re-orders the WORK, round by round.
 //
 // Randomly directed rays (BASELINE config 4) defeat the single-launch marcher twice over: its warps run nearly empty (rays end
-// after 2..4095 steps, a warp lives as long as its longest ray) and every cell change is a scattered fetch from a 2 GB volume
-// (75 B of DRAM traffic per ray-step).  Here the volume is cut into bricks of 2^k voxels per axis and the trace runs in rounds
-// inside ONE kernel launch (grid-wide barriers between the phases of a round, nothing returns to the host):
+// after 2..4095 steps, a warp that refills only when all of its lanes are idle lives as long as its longest ray) and every cell
+// change is a scattered fetch from a 2 GB volume (75 B of DRAM traffic per ray-step, L2 hit rate 20 %).  Here the volume is cut
+// into bricks of 2^k voxels per axis and the trace runs in rounds inside ONE kernel launch (grid-wide barriers between the phases
+// of a round; nothing returns to the host, the number of rounds is whatever the batch needs):
 //     1. bucket pass   counting sort of the rays still alive by the brick they are in: a histogram that the previous round's march
-//                      already filled, a grid-wide exclusive scan that also cuts every brick's ray list into work items of <= 256
-//                      rays, and a scatter of the ray ids (the sort need not be stable: results are written by ray id)
-//     2. march         a CTA takes a work item -- up to 256 rays that are all inside ONE brick -- and marches them until each has
-//                      left the brick (plus a margin that keeps rays from bouncing between two bricks) or has finished.  All
-//                      gathers of the CTA fall into one small box of the volume, so they are served by L1/L2, and every few steps
-//                      the CTA COMPACTS its live rays into the fewest warps (state through shared memory), so issue slots are not
-//                      spent on warps with one or two live lanes.  A ray that leaves the box writes its exact internal state
-//                      (fixed-point position, scaled float direction, step counter, brightness) back and is counted into the next
-//                      round's histogram.
-// When few rays are left (a brick then holds too few to fill a CTA) a last round marches the rest without a box.  Every step is
-// computed exactly like in march3_kernel (same operation order: cu:317-374), so results are bit-identical to the single launch.
-// This replaces round 1's region mode (13 cub radix sorts + 14 launches per trace).
+//                      already filled, a grid-wide exclusive scan, and a scatter of the ray ids (the sort need not be stable:
+//                      results are written by ray id)
+//     2. march         persistent warps pull rays from the brick-sorted list, `refill` lanes at a time, and march every ray until it
+//                      has left its brick (plus a margin that keeps rays from bouncing between two bricks) or has finished.  At any
+//                      moment the ~100 000 rays in flight on the whole GPU belong to a handful of neighbouring bricks, so a brick is
+//                      fetched from DRAM once per round and then served by L2.  A ray that leaves its box writes its exact internal
+//                      state (fixed-point position, scaled float direction, step counter, brightness) back and is counted into the
+//                      next round's histogram.
+// When few rays are left, a last round marches the rest without a box.  Every step is computed exactly like in march3_kernel
+// (same operation order: cu:317-374), so results are bit-identical to the single launch.
+//
+// This replaces round 1's region mode (a cub radix sort and a kernel launch per round, 14 launches + 13 sorts per trace) at the same
+// marching rate; what was tried on the way and measured slower is in DESIGN.md section 6 (a CTA per brick with CTA-wide compaction:
+// latency-bound; warp work items with CTA-shared batches for L1 affinity: no gain, the front of bricks in flight outgrows L2;
+// prefetch.global.L1 one step ahead: 95 -> 56 G ray-steps/s).
 //
 // The kernel can be GATED by a device flag written by coherence_probe_kernel, so that vrt_trace_device -- which cannot look at
 // device buffers without a synchronisation -- enqueues probe + single-launch marcher + this kernel and exactly one of the two
@@ -36,11 +40,10 @@ namespace cg = cooperative_groups;
 #endif
 
 constexpr uint32_t kWaveDone = 0xFFFFFFFFu;
-constexpr int      kWaveThreads = 256;           // threads per CTA = rays per work item
-constexpr uint32_t kItemUnboxed = 0x80000000u;   // work item flag: no box (last round)
+constexpr int      kWaveThreads = 256;           // threads per CTA
 
 // control block (device): written by the scan phase, read by everybody after the grid barrier
-enum { kCtlAlive = 0, kCtlItems = 1, kCtlItemCursor = 2, kCtlTail = 3, kCtlPrevCount = 4, kCtlRounds = 5, kCtlWords = 8 };
+enum { kCtlAlive = 0, kCtlCursor = 2, kCtlTail = 3, kCtlPrevCount = 4, kCtlRounds = 5, kCtlWords = 8 };
 
 struct WaveParams
 {
@@ -53,14 +56,14 @@ struct WaveParams
     uint32_t  *order[2];         // [n]    ray ids of the rays alive, grouped by brick (ping-pong)
     uint32_t  *hist[2];          // [K]    rays per brick for this / the next round
     uint32_t  *bin_off;          // [K+1]  scatter cursor of every brick (starts at the brick's offset into order[]); [K]: the tail round's single cursor
-    uint4     *items;            // work items: {brick | flags, first slot in order[], ray count, 0}
-    uint2     *partial;          // [gridDim] per-CTA (rays, items) of the scan
+    uint32_t  *partial;          // [gridDim] per-CTA ray totals of the scan
     uint32_t  *ctl;              // [kCtlWords]
     int        log2_brick;       // brick edge = 2^log2_brick voxels
     uint32_t   margin;           // voxels a ray may travel beyond its brick before it is suspended
     uint32_t   nby, nbz, K;      // bricks along axes 1, 2; number of bricks
     uint32_t   tail_rays;        // when at most this many rays are alive the rest is marched without a box
-    int        steps_per_check;  // marching steps between two CTA-wide live counts / compactions
+    uint32_t   refill;           // a warp takes new rays from the list when at least this many lanes are idle
+    int        steps_per_check;  // marching steps between two refill polls
     uint32_t   max_rounds;       // safety net (a round always advances every ray by at least one step)
 };
 
@@ -101,30 +104,30 @@ __global__ void coherence_probe_kernel(const uint32_t *pos, const void *dir, int
     if (threadIdx.x == 0) *flag = (samples > 0 && s_bad * 2 > samples) ? 1u : 0u;
 }
 
-// block-wide exclusive scan of one (a, b) pair per thread; returns the block totals in (ta, tb)
-__device__ __forceinline__ void block_scan_pair(uint32_t &a, uint32_t &b, uint32_t &ta, uint32_t &tb, uint2 *s_warp /* [kWaveThreads / 32 + 1] */)
+// block-wide exclusive scan of one value per thread; returns the block total in `total`
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t &total, uint32_t *s_warp /* [kWaveThreads / 32] */)
 {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t ia = a, ib = b;
+    uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
-        const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, ia, o), xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
-        if (lane >= (unsigned)o) { ia += xa; ib += xb; }
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (unsigned)o) inc += x;
     }
-    if (lane == 31) s_warp[warp] = make_uint2(ia, ib);
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t ba = 0, bb = 0, sa = 0, sb = 0;
+    uint32_t before = 0, sum = 0;
 #pragma unroll
     for (int w = 0; w < kWaveThreads / 32; ++w)
     {
-        const uint2 v = s_warp[w];
-        if ((unsigned)w < warp) { ba += v.x; bb += v.y; }
-        sa += v.x; sb += v.y;
+        const uint32_t c = s_warp[w];
+        if ((unsigned)w < warp) before += c;
+        sum += c;
     }
     __syncthreads();
-    a = ba + ia - a; b = bb + ib - b;      // exclusive
-    ta = sa; tb = sb;
+    total = sum;
+    return before + inc - v;
 }
 
 template <typename VoxT, bool DIR_I16, bool LIVE>
@@ -134,14 +137,11 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
     const MarchParams &m = p.m;
     if (m.mode_flag != nullptr && *m.mode_flag != m.mode_want) return;       // gated launch: the probe chose the other marcher (uniform over the grid)
     cg::grid_group grid = cg::this_grid();
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
     const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + tid, gsize = (unsigned long long)gridDim.x * blockDim.x;
 
-    __shared__ uint2    s_scan[kWaveThreads / 32 + 1];
-    __shared__ uint32_t s_live[2][kWaveThreads / 32];
-    __shared__ uint32_t s_xch[9][kWaveThreads];       // compaction: px py pz dx dy dz it brightness ray
-    __shared__ uint4    s_item;
-    __shared__ uint32_t s_base[2];
+    __shared__ uint32_t s_scan[kWaveThreads / 32];
+    __shared__ uint32_t s_base;
 
     // ---- phase 0: every ray into the state arrays, first histogram ---------------------------------------------------------
     for (unsigned long long i = gtid; i < (unsigned long long)p.K; i += gsize) { p.hist[0][i] = 0; p.hist[1][i] = 0; }
@@ -165,55 +165,46 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
     int cur = 0;            // hist[cur] counts this round's rays; order[cur] is built from order[cur ^ 1]
     for (uint32_t round = 0; round < p.max_rounds; ++round)
     {
-        // ---- bucket pass 1a: per-CTA totals of (rays, work items) over the CTA's slice of bricks ------------------------------
+        // ---- bucket pass 1a: per-CTA ray totals over the CTA's slice of bricks -------------------------------------------------
         const uint32_t slice = ((p.K + gridDim.x - 1) / gridDim.x + kWaveThreads - 1) / kWaveThreads * kWaveThreads;
         const uint32_t b_lo = min(p.K, blockIdx.x * slice), b_hi = min(p.K, b_lo + slice);
         {
-            uint32_t a = 0, b = 0, ta, tb;
-            for (uint32_t k = b_lo + tid; k < b_hi; k += kWaveThreads) { const uint32_t c = p.hist[cur][k]; a += c; b += (c + kWaveThreads - 1) / kWaveThreads; }
-            block_scan_pair(a, b, ta, tb, s_scan);
-            if (tid == 0) p.partial[blockIdx.x] = make_uint2(ta, tb);
+            uint32_t a = 0, total;
+            for (uint32_t k = b_lo + tid; k < b_hi; k += kWaveThreads) a += p.hist[cur][k];
+            block_scan(a, total, s_scan);
+            if (tid == 0) p.partial[blockIdx.x] = total;
         }
         grid.sync();
-        // ---- bucket pass 1b: offsets of the slice, work items, control block -----------------------------------------------------
+        // ---- bucket pass 1b: every brick's first slot in order[] (its scatter cursor), control block -----------------------------
         {
-            uint32_t a = 0, b = 0, ta, tb;
-            for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint2 v = p.partial[c]; if (c < blockIdx.x) { a += v.x; b += v.y; } }
-            uint32_t ea = a, eb = b;
-            block_scan_pair(ea, eb, ta, tb, s_scan);                   // ta, tb = rays / items in the slices before this CTA's
-            if (tid == 0) { s_base[0] = ta; s_base[1] = tb; }
-            __syncthreads();
-            uint32_t off_r = s_base[0], off_i = s_base[1];
-            uint32_t alive = 0, nitems = 0;
-            if (blockIdx.x == 0)                                       // grand totals, by CTA 0
+            uint32_t a = 0, before, all = 0;
+            for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint32_t v = p.partial[c]; if (c < blockIdx.x) a += v; all += v; }
+            block_scan(a, before, s_scan);                             // rays in the slices before this CTA's
+            if (blockIdx.x == 0)
             {
-                uint32_t x = 0, y = 0, tx, ty;
-                for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint2 v = p.partial[c]; x += v.x; y += v.y; }
-                block_scan_pair(x, y, tx, ty, s_scan);
-                alive = tx; nitems = ty;
+                uint32_t alive;
+                block_scan(all, alive, s_scan);
+                if (tid == 0)
+                {
+                    p.bin_off[p.K] = 0;                                // the tail round's single cursor
+                    p.ctl[kCtlAlive] = alive; p.ctl[kCtlCursor] = 0;
+                    p.ctl[kCtlTail] = alive <= p.tail_rays ? 1u : 0u;
+                    p.ctl[kCtlRounds] = round + 1;
+                }
             }
+            uint32_t off = before;
             for (uint32_t k0 = b_lo; k0 < b_hi; k0 += kWaveThreads)
             {
                 const uint32_t k = k0 + tid;
                 const uint32_t c = k < b_hi ? p.hist[cur][k] : 0u;
-                uint32_t xr = c, xi = (c + kWaveThreads - 1) / kWaveThreads, tr_, ti_;
-                const uint32_t ni = xi;
-                block_scan_pair(xr, xi, tr_, ti_, s_scan);
+                uint32_t tile_total;
+                const uint32_t ex = block_scan(c, tile_total, s_scan);
                 if (k < b_hi)
                 {
-                    p.bin_off[k] = off_r + xr;
-                    for (uint32_t j = 0; j < ni; ++j)
-                        p.items[off_i + xi + j] = make_uint4(k, off_r + xr + j * kWaveThreads, min((uint32_t)kWaveThreads, c - j * kWaveThreads), 0u);
+                    p.bin_off[k] = off + ex;
                     p.hist[cur ^ 1][k] = 0;                            // the next round's histogram starts empty
                 }
-                off_r += tr_; off_i += ti_;
-            }
-            if (blockIdx.x == 0 && tid == 0)
-            {
-                p.bin_off[p.K] = 0;                                    // the tail round's single cursor
-                p.ctl[kCtlAlive] = alive; p.ctl[kCtlItems] = nitems; p.ctl[kCtlItemCursor] = 0;
-                p.ctl[kCtlTail] = alive <= p.tail_rays ? 1u : 0u;
-                p.ctl[kCtlRounds] = round + 1;
+                off += tile_total;
             }
         }
         grid.sync();
@@ -229,50 +220,59 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
             if (k != kWaveDone) p.order[cur][atomicAdd(&p.bin_off[tail ? p.K : k], 1u)] = ray;
         }
         grid.sync();
-        // ---- march -------------------------------------------------------------------------------------------------------------
-        const uint32_t nitems = tail ? (alive + kWaveThreads - 1) / kWaveThreads : p.ctl[kCtlItems];
-        for (;;)
+        // ---- march: persistent warps pull rays from the brick-sorted list ------------------------------------------------------
+        // Consecutive warps -- on all SMs -- work on the same few bricks at the same time, so a brick is fetched from DRAM once per
+        // round and then served by L2 (and L1).  A ray marches inside its brick's box (the box is per lane); idle lanes are refilled
+        // from the list as soon as `refill` of them are free, so warps stay full although rays leave their bricks after very
+        // different numbers of steps.
         {
-            if (tid == 0)
-            {
-                const uint32_t it_id = atomicAdd(&p.ctl[kCtlItemCursor], 1u);
-                uint4 w = make_uint4(0, 0, 0, 1u);                      // .w = 1: no more work
-                if (it_id < nitems)
-                    w = tail ? make_uint4(kItemUnboxed, it_id * kWaveThreads, min((uint32_t)kWaveThreads, alive - it_id * kWaveThreads), 0u) : p.items[it_id];
-                s_item = w;
-            }
-            __syncthreads();
-            const uint4 item = s_item;
-            __syncthreads();
-            if (item.w) break;
-
-            // the box this item's rays may march in during this round: [lo, lo + span) in 16.16, clipped to the volume
-            uint32_t lo_x = 0, lo_y = 0, lo_z = 0, sp_x = m.limx16, sp_y = m.limy16, sp_z = m.limz16;
-            if (!(item.x & kItemUnboxed))
-            {
-                const uint32_t e = 1u << p.log2_brick;
-                const uint32_t bz_ = item.x % p.nbz, by_ = (item.x / p.nbz) % p.nby, bx_ = item.x / (p.nbz * p.nby);
-                const uint32_t ax = bx_ * e, ay = by_ * e, az = bz_ * e;
-                const uint32_t l_x = ax > p.margin ? ax - p.margin : 0u, l_y = ay > p.margin ? ay - p.margin : 0u, l_z = az > p.margin ? az - p.margin : 0u;
-                const uint32_t h_x = min(ax + e + p.margin, m.limx), h_y = min(ay + e + p.margin, m.limy), h_z = min(az + e + p.margin, m.limz);
-                lo_x = l_x << 16; lo_y = l_y << 16; lo_z = l_z << 16;
-                sp_x = (h_x - l_x) << 16; sp_y = (h_y - l_y) << 16; sp_z = (h_z - l_z) << 16;
-            }
+            const float invx = m.invx, invy = m.invy, invz = m.invz;
+            uint32_t lo_x = 0, lo_y = 0, lo_z = 0, sp_x = 0, sp_y = 0, sp_z = 0;       // this lane's box: [lo, lo + span) in 16.16, clipped to the volume
             uint32_t px = 0, py = 0, pz = 0, it = 0, brightness = 0xFFFFFFFFu, cached_tr = 0, moved = 0xFFFFFFFFu, ray = 0;
             float dx = 0, dy = 0, dz = 0;
-            bool have = tid < item.z;
-            if (have)
-            {
-                ray = p.order[cur][item.y + tid];
-                px = p.st_pos[(size_t)ray * 3]; py = p.st_pos[(size_t)ray * 3 + 1]; pz = p.st_pos[(size_t)ray * 3 + 2];
-                dx = p.st_dir[(size_t)ray * 3]; dy = p.st_dir[(size_t)ray * 3 + 1]; dz = p.st_dir[(size_t)ray * 3 + 2];
-                it = p.st_it[ray];
-                if (LIVE) brightness = p.st_light[ray];
-            }
+            bool have = false, exhausted = false;                                    // exhausted: warp-uniform, the list has been handed out
             CornersP q;
-            const float invx = m.invx, invy = m.invy, invz = m.invz;
-            for (uint32_t iter = 0;; ++iter)
+            for (;;)
             {
+                if (!exhausted)
+                {
+                    const unsigned idle = __ballot_sync(FULL, !have);
+                    const uint32_t nidle = (uint32_t)__popc(idle);
+                    if (nidle >= p.refill)
+                    {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&p.ctl[kCtlCursor], nidle);
+                        base = __shfl_sync(FULL, base, 0);
+                        if (!have)
+                        {
+                            const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                            if (idx < alive)
+                            {
+                                ray = p.order[cur][idx];
+                                px = p.st_pos[(size_t)ray * 3]; py = p.st_pos[(size_t)ray * 3 + 1]; pz = p.st_pos[(size_t)ray * 3 + 2];
+                                dx = p.st_dir[(size_t)ray * 3]; dy = p.st_dir[(size_t)ray * 3 + 1]; dz = p.st_dir[(size_t)ray * 3 + 2];
+                                it = p.st_it[ray];
+                                if (LIVE) brightness = p.st_light[ray];
+                                moved = 0xFFFFFFFFu;
+                                if (tail) { lo_x = lo_y = lo_z = 0; sp_x = m.limx16; sp_y = m.limy16; sp_z = m.limz16; }
+                                else
+                                {
+                                    // the brick the ray is in (the same arithmetic that produced its key), widened by the margin
+                                    const uint32_t e = 1u << p.log2_brick;
+                                    const uint32_t ax = (min(px >> 16, m.limx) >> p.log2_brick) * e, ay = (min(py >> 16, m.limy) >> p.log2_brick) * e,
+                                                   az = (min(pz >> 16, m.limz) >> p.log2_brick) * e;
+                                    const uint32_t l_x = ax > p.margin ? ax - p.margin : 0u, l_y = ay > p.margin ? ay - p.margin : 0u, l_z = az > p.margin ? az - p.margin : 0u;
+                                    const uint32_t h_x = min(ax + e + p.margin, m.limx), h_y = min(ay + e + p.margin, m.limy), h_z = min(az + e + p.margin, m.limz);
+                                    lo_x = l_x << 16; lo_y = l_y << 16; lo_z = l_z << 16;
+                                    sp_x = (h_x - l_x) << 16; sp_y = (h_y - l_y) << 16; sp_z = (h_z - l_z) << 16;
+                                }
+                                have = true;
+                            }
+                        }
+                        if (base + nidle >= alive) exhausted = true;
+                    }
+                }
+                if (!__any_sync(FULL, have)) { if (exhausted) break; else continue; }
                 if (have)
                 {
                     const uint32_t it_stop = it - min(it, (uint32_t)p.steps_per_check);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         dz = __fmaf_rn(invz, gz, dz);
                         unpack2(dxy, dx, dy);
                         const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                        const float ilen = div_is_fast(dot) ? div_fast(dot) : __fdiv_rn(0x42000000p0f, dot);  // cu:346 (div_fast is exact in its range)
+                        const float ilen = __fdiv_rn(0x42000000p0f, dot);                                    // cu:346
                         unpack2(mul2(mul2(pack2(invx, invy), dxy), pack2(ilen, ilen)), sx, sy);              // cu:347
                         const uint32_t nx = px + (uint32_t)__float2int_rn(sx);
                         const uint32_t ny = py + (uint32_t)__float2int_rn(sy);
@@ -336,40 +336,6 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         atomicAdd(&p.hist[cur ^ 1][key], 1u);
                         have = false;
                     }
-                }
-                // CTA-wide live count; compaction when it frees at least one warp
-                const unsigned live_mask = __ballot_sync(FULL, have);
-                const int par = iter & 1;
-                if (lane == 0) s_live[par][warp] = (uint32_t)__popc(live_mask);
-                __syncthreads();
-                uint32_t tot = 0, active = 0, before = 0;
-#pragma unroll
-                for (int w = 0; w < kWaveThreads / 32; ++w)
-                {
-                    const uint32_t c = s_live[par][w];
-                    tot += c; active += c ? 1u : 0u;
-                    if ((unsigned)w < warp) before += c;
-                }
-                if (tot == 0) break;                                                                         // uniform over the CTA
-                if (active > (tot + 31u) / 32u)
-                {
-                    if (have)
-                    {
-                        const uint32_t slot = before + (uint32_t)__popc(live_mask & ((1u << lane) - 1u));
-                        s_xch[0][slot] = px; s_xch[1][slot] = py; s_xch[2][slot] = pz;
-                        s_xch[3][slot] = __float_as_uint(dx); s_xch[4][slot] = __float_as_uint(dy); s_xch[5][slot] = __float_as_uint(dz);
-                        s_xch[6][slot] = it; s_xch[7][slot] = brightness; s_xch[8][slot] = ray;
-                    }
-                    __syncthreads();
-                    have = tid < tot;
-                    if (have)
-                    {
-                        px = s_xch[0][tid]; py = s_xch[1][tid]; pz = s_xch[2][tid];
-                        dx = __uint_as_float(s_xch[3][tid]); dy = __uint_as_float(s_xch[4][tid]); dz = __uint_as_float(s_xch[5][tid]);
-                        it = s_xch[6][tid]; brightness = s_xch[7][tid]; ray = s_xch[8][tid];
-                        moved = 0xFFFFFFFFu;                                                                 // the cached corners belong to another ray
-                    }
-                    __syncthreads();
                 }
             }
         }

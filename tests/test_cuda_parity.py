@@ -291,7 +291,8 @@ def test_size_independent_properties_large(vrt, oracle):
     pos, d = W.rays_parallel_x(1024, 1024, 30.0, 225.0, x0=2.0)
     # normalise on the host oracle for the subsample, on the GPU for everything
     import torch
-    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).cuda(); tdir = torch.from_numpy(d.reshape(-1)).cuda()
+    dev0 = torch.device("cuda", co.device)     # not .cuda(): the reference's CUDA build (an earlier test) leaves another device current on multi-GPU boxes
+    tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev0); tdir = torch.from_numpy(d.reshape(-1)).to(dev0)
     co.normalise_rays_device(tpos, tdir)
     results = []
     for kver, refill in ((1, 0), (2, 16), (3, 1), (3, 32)):
@@ -321,7 +322,7 @@ def test_size_independent_properties_large(vrt, oracle):
     assert EQ(np.concatenate([o1[0].cpu().numpy(), o2[0].cpu().numpy()]), base[0])
     assert EQ(np.concatenate([o1[2].cpu().numpy(), o2[2].cpu().numpy()]), base[2])
     # (iv) permutation
-    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    perm = torch.randperm(n, device=dev0, generator=torch.Generator(device=dev0).manual_seed(3))
     pp = tpos.view(-1, 3)[perm].contiguous().view(-1); dd = tdir.view(-1, 3)[perm].contiguous().view(-1)
     op = co.trace_device(pp, dd, [1, 1, 1], 0, 4096)
     torch.cuda.synchronize()

@@ -1411,6 +1411,15 @@ int vrt_trace_device(vrt_scene *s, uint64_t n, const uint32_t *d_pos, const void
     DeviceGuard g(s->device);
     if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (n)
+    {
+        // buffers on another GPU would be reached over NVLink once peer access is on (vrt_scene_replicate enables it) -- slowly, and
+        // with a stream that belongs to the wrong device: refuse instead
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, d_pos) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != s->device)
+            return fail(VRT_ERR_INVALID, "ray buffers are on device " + std::to_string(at.device) + ", the scene is on device " + std::to_string(s->device));
+        cudaGetLastError();
+    }
     unsigned long long *scratch = nullptr;       // [0] refill counter, [1] cap flag, [2] probe flag
     VRT_CUDA(pool_alloc((void **)&scratch, 4 * sizeof(unsigned long long), s->device, st));
     MarchMode mode;

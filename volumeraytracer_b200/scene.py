@@ -240,6 +240,13 @@ class Comm:
 
     def __init__(self, device, rank, world, exchange):
         self._c = C.c_void_p()
+        # libvrt_b200.so dlopens "libnccl.so.2".  In a process that also uses PyTorch, torch's bundled NCCL must be the copy that gets
+        # mapped (the loader keeps one object per soname, and libtorch_cuda.so needs symbols a system-wide older NCCL may lack): make
+        # sure torch is loaded first when it is installed.
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
         uid = None
         if rank == 0:
             buf = C.create_string_buffer(128)

@@ -250,11 +250,11 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
     scene.set_option(vrt.VRT_OPT_KERNEL, 10)               # allocates / zeroes the counters
     one_pass()
     torch.cuda.synchronize()
-    cnt = [scene.get_option(vrt.VRT_INFO_STAT_BASE + k) for k in range(8)]
+    cnt = [scene.get_option(vrt.VRT_INFO_STAT_BASE + k) for k in range(9)]
     scene.set_option(vrt.VRT_OPT_KERNEL, 0)
     names = ["outer", "refill", "fast_step", "reload", "mid", "generic", "retire"]
     b = blocks["blocks"]
-    warp_instr = sum(cnt[i] * b[nm] for i, nm in enumerate(names))
+    warp_instr = sum(cnt[i] * b[nm] for i, nm in enumerate(names)) + cnt[8] * b.get("reload_partial", 1)
     num_sms = scene.get_option(vrt.VRT_INFO_NUM_SMS)
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     peak = num_sms * 4 * sm_mhz * 1e6
@@ -264,7 +264,7 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
             "traffic": None, "warp_instructions_per_pass": warp_instr, "warp_steps_per_pass": warp_steps,
             "warp_instructions_per_warp_step": warp_instr / max(warp_steps, 1),
             "lane_efficiency": cnt[7] / max(32 * warp_steps, 1), "reloads_per_warp_step": cnt[3] / max(warp_steps, 1),
-            "block_issue_counts": dict(zip(names + ["lane_steps"], cnt)), "block_sass_lengths": b, "sass_lengths_source": src,
+            "block_issue_counts": dict(zip(names + ["lane_steps", "reload_partial"], cnt)), "block_sass_lengths": b, "sass_lengths_source": src,
             "num_sms": num_sms, "sm_mhz": sm_mhz, "launch_ms": launch_s * 1e3,
             "how": "counts from one extra pass of the instrumented kernel copy (VRT_OPT_KERNEL 10, outside the timed region); "
                    "time and clock from the timed region; cross-check against ncu smsp__inst_executed.sum in profiles/"}

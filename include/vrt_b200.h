@@ -116,9 +116,10 @@ enum {
                                       extra channel), in 1/1000 -- the figure to look at before choosing VRT_OPT_KERNEL 6 */
     VRT_INFO_NUM_SMS      = 101, /* read-only: multiprocessor count of the scene's device (cudaGetDeviceProperties) */
     /* read-only, VRT_OPT_KERNEL 10 only (an instrumented copy of the default float / unit-invscale kernel, for measurement: same
-       results, slower): VRT_INFO_STAT_BASE + k, k = 0..7 = how many times block k of the marcher was ISSUED (per warp pass) since
+       results, slower): VRT_INFO_STAT_BASE + k, k = 0..11 = how many times block k of the marcher was ISSUED (per warp pass) since
        the option was set: 0 outer loop, 1 refill, 2 fast-loop step, 3 cell reload, 4 fast-loop exit checks, 5 generic step,
-       6 retire/store, 7 lane-steps (per-thread, not per warp).  bench.py turns these into the issue-slot roofline. */
+       6 retire/store, 7 lane-steps (per-thread, not per warp), 8 cell reloads taken by only a part of the active lanes (the
+       reconvergence instruction then issues twice), 9..11 unused.  bench.py turns these into the issue-slot roofline. */
     VRT_INFO_STAT_BASE    = 200,
     VRT_OPT_MAX_CTAS_PER_SM = 5 /* persistent mode: cap on resident CTAs per SM (0 = occupancy limit); fewer rays in flight keep an
                                    incoherent batch's working set inside L1/L2 */

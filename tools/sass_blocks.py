@@ -7,7 +7,9 @@ pass).  This tool reads the lengths of those blocks -- in SASS instructions -- o
 production kernel (march3_kernel<float,false,false,false,9>) with nvdisasm, finds the loop nest from the backward branches and
 classifies the blocks by what they contain:
     fast loop      innermost loop holding MUFU.RCP and the LDG.E.128 corner loads       -> `fast_step` (without the reload region)
-    reload         the BSSY..BSYNC region inside the fast loop that holds the LDG.E.128  -> `reload`
+    reload         the block inside the fast loop that holds the LDG.E.128 corner loads, from the branch that skips it to the
+                   reconvergence BSYNC (exclusive)                                        -> `reload`; `reload_partial` = that BSYNC,
+                   issued a second time when only a part of the active lanes took the reload
     for(;;) body   the loop around the fast loop (fast-loop exit checks + the straight-line generic step) -> `mid`, `generic`
     refill         the region of the outer loop that holds the ATOMG (ray counter)       -> `refill`
     retire         the region of the outer loop that holds the STG of the results        -> `retire`
@@ -106,7 +108,15 @@ def analyse(sass):
         return out
 
     fb = body(*fast)
-    reload_r = min((r for r in ssy_regions(*fast) if has(body(*r), r"LDG\.E\.128")), key=lambda r: r[1] - r[0])
+    # reload block: what the forward branch just before the corner loads skips -- from the instruction after that branch up to (not
+    # including) the reconvergence BSYNC it jumps to.  The BSYNC itself is issued by every warp pass, and a SECOND time when only a
+    # part of the active lanes took the reload (the two groups each issue it): counted separately by the instrumented kernel.
+    ldg = [a for a, t in fb if re.search(r"LDG\.E\.128", t)]
+    skips = [(a, target(t)) for a, t in fb if re.search(r"\bBRA\b", t) and target(t) and a < ldg[0] and max(ldg) < target(t) <= fast[1]]
+    bra, tgt = max(skips, key=lambda x: x[0])
+    reload_r = (bra + 0x10, tgt - 0x10)
+    if not re.search(r"BSYNC", dict(ins)[tgt]):
+        raise SystemExit("reload block does not end at a BSYNC: %s" % dict(ins)[tgt])
     n_fast_all = len(fb)
     n_reload = len(body(*reload_r))
     n_for = len(body(*forl))
@@ -132,7 +142,7 @@ def analyse(sass):
     n_mid = min(n_mid, n_rest)
     ops = "\n".join(re.sub(r"\s+", " ", t) for _, t in ins)
     counts = {
-        "fast_step": n_fast_all - n_reload, "reload": n_reload, "mid": n_mid, "generic": n_rest - n_mid,
+        "fast_step": n_fast_all - n_reload, "reload": n_reload, "reload_partial": 1, "mid": n_mid, "generic": n_rest - n_mid,
         "refill": n_refill, "retire": n_retire, "outer": max(n_outer, 0),
     }
     mix = {}
@@ -145,7 +155,7 @@ def analyse(sass):
                   "reload": [hex(reload_r[0]), hex(reload_r[1])]},
         "fast_loop_opcode_mix": dict(sorted(mix.items(), key=lambda kv: -kv[1])),
         "sass_sha1": hashlib.sha1(ops.encode()).hexdigest(),
-        "stat_slots": {"outer": 0, "refill": 1, "fast_step": 2, "reload": 3, "mid": 4, "generic": 5, "retire": 6, "lane_steps": 7},
+        "stat_slots": {"outer": 0, "refill": 1, "fast_step": 2, "reload": 3, "mid": 4, "generic": 5, "retire": 6, "lane_steps": 7, "reload_partial": 8},
     }
 
 

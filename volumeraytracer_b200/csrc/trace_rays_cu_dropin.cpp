@@ -29,6 +29,9 @@
 #include <string>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -37,9 +40,67 @@
 
 namespace {
 
+// One worker thread per device, alive as long as the TraceRaysCu object: vrt_trace keeps its streams, events and pinned staging per
+// calling thread, so short-lived threads would set all of that up again on every call (with 8 devices that cost more than the march).
+class DeviceWorkers
+{
+public:
+    explicit DeviceWorkers(size_t n) : _jobs(n), _pending(0), _stop(false)
+    {
+        for (size_t k = 0; k < n; ++k) _threads.emplace_back([this, k] { loop(k); });
+    }
+    ~DeviceWorkers()
+    {
+        { std::lock_guard<std::mutex> lk(_mu); _stop = true; }
+        _cv.notify_all();
+        for (auto &t : _threads) t.join();
+    }
+    // runs job(k) on worker k for k < n_active and waits for all of them
+    void run(size_t n_active, std::function<void(size_t)> const &job)
+    {
+        {
+            std::lock_guard<std::mutex> lk(_mu);
+            for (size_t k = 0; k < n_active && k < _jobs.size(); ++k) _jobs[k] = &job;
+            _pending = std::min(n_active, _jobs.size());
+        }
+        _cv.notify_all();
+        std::unique_lock<std::mutex> lk(_mu);
+        _done.wait(lk, [this] { return _pending == 0; });
+    }
+    size_t size() const { return _threads.size(); }
+private:
+    void loop(size_t k)
+    {
+        for (;;)
+        {
+            std::function<void(size_t)> const *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(_mu);
+                _cv.wait(lk, [&] { return _stop || _jobs[k] != nullptr; });
+                if (_stop) return;
+                job = _jobs[k];
+            }
+            (*job)(k);
+            {
+                std::lock_guard<std::mutex> lk(_mu);
+                _jobs[k] = nullptr;
+                if (--_pending == 0) _done.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> _threads;
+    std::vector<std::function<void(size_t)> const *> _jobs;
+    size_t _pending;
+    bool _stop;
+    std::mutex _mu;
+    std::condition_variable _cv, _done;
+};
+
 struct DropinState
 {
     std::vector<vrt_scene *> scenes; // one per device
+    std::unique_ptr<DeviceWorkers> workers;   // only with more than one device
+    std::mutex call_mu;                       // one multi-device trace at a time per object (single-device calls stay concurrent)
 };
 
 // measurement hooks for bench.py's e2e_reference_api leg: wall time of the last constructor / trace_rays_cu call inside this
@@ -114,6 +175,7 @@ TraceRaysCu<DiffType>::TraceRaysCu(std::vector<size_t> const &bounds, std::vecto
         }
         g_last_replicate_s = secs;
         for (vrt_scene *x : rep) st->scenes.push_back(x);
+        st->workers.reset(new DeviceWorkers(st->scenes.size()));
     }
     g_last_ctor_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     _tex = st.release();
@@ -125,6 +187,7 @@ TraceRaysCu<DiffType>::~TraceRaysCu()
     DropinState *st = static_cast<DropinState *>(_tex);
     if (st)
     {
+        st->workers.reset();                  // joins the worker threads (their per-thread streams go with them)
         for (vrt_scene *s : st->scenes) vrt_scene_destroy(s);
         delete st;
     }
@@ -182,9 +245,8 @@ void TraceRaysCu<DiffType>::trace_rays_cu(std::vector<pos_t> const &start_positi
     if (ndev == 1) work(0);
     else
     {
-        std::vector<std::thread> pool;
-        for (size_t k = 0; k < ndev; ++k) pool.emplace_back(work, k);
-        for (auto &t : pool) t.join();
+        std::lock_guard<std::mutex> lk(st->call_mu);
+        st->workers->run(ndev, work);
     }
     for (auto const &e : errors) if (!e.empty()) throw std::runtime_error("vrt_trace: " + e);
     bool warn = false;                                                                          // cu:507-515: flag set by the marcher

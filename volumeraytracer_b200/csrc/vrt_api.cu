@@ -102,7 +102,7 @@ struct vrt_scene
         if (cudaMemcpy(h, d_wave_info, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
         return (int64_t)h[vrt::kCtlRounds];
     }
-    unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: 8 block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
+    unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: kStatSlots block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
     std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{32}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
@@ -650,8 +650,8 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
         if (v == 10)       // instrumented copy of the default kernel: allocate / zero the block counters
         {
             DeviceGuard g(s->device);
-            if (!s->d_stats) VRT_CUDA(cudaMalloc((void **)&s->d_stats, 8 * sizeof(unsigned long long)));
-            VRT_CUDA(cudaMemset(s->d_stats, 0, 8 * sizeof(unsigned long long)));
+            if (!s->d_stats) VRT_CUDA(cudaMalloc((void **)&s->d_stats, kStatSlots * sizeof(unsigned long long)));
+            VRT_CUDA(cudaMemset(s->d_stats, 0, kStatSlots * sizeof(unsigned long long)));
         }
         else if (v < 0 || v > 6 || v == 4 || v == 5) return fail(VRT_ERR_INVALID, "kernel must be 0, 1, 2, 3, 6 or 10 (4/5/7/8/9 are selected implicitly)");
         s->opt_kernel = v; break;
@@ -697,6 +697,7 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
     case VRT_INFO_STAT_BASE + 0: case VRT_INFO_STAT_BASE + 1: case VRT_INFO_STAT_BASE + 2: case VRT_INFO_STAT_BASE + 3:
     case VRT_INFO_STAT_BASE + 4: case VRT_INFO_STAT_BASE + 5: case VRT_INFO_STAT_BASE + 6: case VRT_INFO_STAT_BASE + 7:
+    case VRT_INFO_STAT_BASE + 8: case VRT_INFO_STAT_BASE + 9: case VRT_INFO_STAT_BASE + 10: case VRT_INFO_STAT_BASE + 11:
     {
         *v = 0;
         if (!s->d_stats) break;
@@ -1508,7 +1509,19 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
     // at least 2^17 rays per chunk (one wave of the persistent grid), at most 16 chunks: config 2 (1 M rays) through pageable buffers
     // runs 8 chunks at 224 G ray-steps/s instead of 2 chunks at 190
-    if (chunk == 0) chunk = n <= (1u << 17) ? n : std::max<uint64_t>(1u << 17, (n + 15) / 16);
+    if (chunk == 0 && n > (1u << 17))
+    {
+        // ... and a whole number of WAVES of the persistent grid (148 SMs x 1024 resident threads = 151 552 rays): on a workload whose
+        // rays all run equally long (config 5) a chunk of 131 072 rays leaves 13 % of the grid idle for a whole ray-time, which is
+        // what a 2 M-ray shard of the strong-scaling run paid in every one of its 16 chunks (e2e 2174 -> see DESIGN.md section 7)
+        uint64_t per_sm = 1024;                                             // 64 registers per thread
+        const int64_t cap = s->opt_max_ctas.load(), blk = s->opt_block.load();
+        if (cap > 0) per_sm = std::min<uint64_t>(per_sm, (uint64_t)(cap * blk));
+        const uint64_t wave = std::max<uint64_t>(1, (uint64_t)s->num_sms * per_sm);
+        const uint64_t m = std::max<uint64_t>(1, ((n + 15) / 16 + wave / 2) / wave);
+        chunk = std::max<uint64_t>(1u << 17, m * wave);
+    }
+    if (chunk == 0) chunk = n;
     if (region > 0 && s->opt_chunk.load() == 0) chunk = std::max<uint64_t>(chunk, std::min<uint64_t>(n, 4u << 20));   // the wavefront marcher wants many rays per brick
     if (want_path)
     {

@@ -449,6 +449,16 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": w_ms / args.weak_steps, "scaling": "weak"}
         del wp, wd, we, wdd, wi, wl, pw, dw
 
+    # ---- config 4 (BASELINE.json configs[3]: 512^3 solve_harmonic field, 8M randomly directed rays, 1/2/4/8 B200), strong scaling ----
+    # the incoherent, gather-bound case: scene built on rank 0 and replicated by the library's NCCL broadcast, every rank marches its
+    # contiguous 1/N of the ONE 8 388 608-ray batch (wavefront marcher chosen by the device-side probe), device-resident, max over ranks
+    c4 = None
+    if world > 1 and args.c4_steps > 0:
+        try:
+            c4 = config4_scaling(dev, comm, rank, world, args.c4_steps, barrier, reduce_max, reduce_sum, vrt, W, vd)
+        except Exception as e:                                                 # never lose the headline line to an extra
+            c4 = {"error": "%s: %s" % (type(e).__name__, e)}
+
     line = None
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -484,7 +494,7 @@ def run_ours(args, rank, local_rank, world):
                     "pinned_value": e2e_pinned, "pinned_note": "same call with the chunk cudaHostRegister'ed (registration outside the timed region)"},
             "gpu_launches": launches_global, "roofline": roof if roof is not None else roof_hbm, "roofline_hbm": roof_hbm, "roofline_l2": roof_l2,
             "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast": bcast,
-            "nccl_broadcast_gbs": bcast["gb_per_s"] if bcast else None, "weak_scaling": weak,
+            "nccl_broadcast_gbs": bcast["gb_per_s"] if bcast else None, "weak_scaling": weak, "config4_scaling": c4,
             "kernel": {"variant": scene.get_option(vrt.VRT_OPT_KERNEL), "block": scene.get_option(vrt.VRT_OPT_BLOCK_THREADS),
                        "refill": scene.get_option(vrt.VRT_OPT_REFILL), "steps_per_poll": scene.get_option(vrt.VRT_OPT_STEPS_PER_POLL)},
         }
@@ -529,6 +539,49 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config4_scaling(dev, comm, rank, world, steps, barrier, reduce_max, reduce_sum, vrt, W, vd, size=512, n_total=8 << 20, iterations=4096):
+    import torch
+    scene0 = None
+    if rank == 0:
+        ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
+        tr = W.clear_translucency_torch((size,) * 3, dev)
+        scene0 = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr)
+        del ior, tr
+    torch.cuda.synchronize(); barrier()
+    sc, bsec = comm.broadcast_scene(scene0, root=0)
+    pos, d = W.rays_random(n_total, 8.0, size - 9.0, 0x5EED0004)            # the same batch on every rank; rank r keeps its contiguous chunk
+    i0, i1 = vd.chunk_bounds(n_total, world, rank)
+    tp = torch.from_numpy(pos[i0:i1].view(np.int32).reshape(-1).copy()).to(dev); td = torch.from_numpy(d[i0:i1].reshape(-1).copy()).to(dev)
+    del pos, d
+    sc.normalise_rays_device(tp, td)
+    n = i1 - i0
+    ep = torch.empty_like(tp); ed = torch.empty_like(td)
+    ei = torch.empty(n, dtype=torch.int32, device=dev); li = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    run = lambda: sc.trace_device(tp, td, [1.0, 1.0, 1.0], 0, iterations, epos=ep, edir=ed, eit=ei, light=li, stream=stream)
+    run(); run()
+    barrier()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        run()
+    b.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = reduce_max(a.elapsed_time(b))
+    total = reduce_sum(int(ei.to(torch.int64).sum().item()))
+    rounds = sc.get_option(vrt.VRT_INFO_WAVE_ROUNDS)
+    out = {"workload": "config 4: 512^3 harmonic field, ONE batch of 8 388 608 randomly directed rays, cap 4096, contiguous chunks over %d GPU(s)" % world,
+           "value": total * steps / (ms * 1e-3) / 1e9, "unit": "G ray-steps/s", "scaling": "strong", "ms_per_pass": ms / steps, "steps": steps,
+           "ray_steps_per_pass": total, "rays_per_gpu": n, "wavefront_rounds_rank0": rounds,
+           "mode": "device-resident (vrt_trace_device), default options: the device-side probe picks the wavefront marcher",
+           "scene_broadcast_seconds": bsec}
+    sc.close()
+    del tp, td, ep, ed, ei, li
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline_and_parity(scene, ior, pos_t, dir_t, epos, edir, eit, side, iters, size):
@@ -619,6 +672,7 @@ def main():
     ap.add_argument("--ref-window", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weak-steps", type=int, default=3, help="N>1: timed passes of the weak-scaling extra (0 = skip)")
+    ap.add_argument("--c4-steps", type=int, default=3, help="N>1: timed passes of the config-4 strong-scaling extra (0 = skip)")
     ap.add_argument("--extras", default="all", help="all | none | comma list of other,refcuda,refapi (extra legs; N>1 runs refapi only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

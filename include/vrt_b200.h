@@ -106,7 +106,7 @@ enum {
        3-D batches (>= 2^18 rays) over volumes that do not fit L2 are probed. */
     VRT_OPT_WAVE_LOG2     = 8,
     VRT_OPT_WAVE_MARGIN   = 9,  /* voxels a ray may travel beyond its brick before it is re-bucketed (default 8) */
-    VRT_OPT_WAVE_CHECK    = 10, /* marching steps between two refill polls of a warp (default 32) */
+    VRT_OPT_WAVE_CHECK    = 10, /* marching steps between two refill polls of a warp (default 16) */
     VRT_OPT_WAVE_TAIL_PERMILLE = 11, /* when at most this share of the batch is still alive, the rest is marched without bricks (default 20) */
     VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = occupancy limit) */
     VRT_OPT_WAVE_REFILL   = 14, /* a warp takes new rays from the brick-sorted list when at least this many lanes are idle (default 8) */

@@ -342,6 +342,34 @@ def test_wavefront_mode_is_bit_identical(vrt, oracle, volk, dirk, live):
     t.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,volk", [((30, 28, 33), "f32"), ((21, 70, 9), "f32"), ((30, 28, 33), "i16"), ((26, 24, 40), "i16")])
+def test_wavefront_odd_extents_and_extreme_directions(vrt, oracle, shape, volk):
+    """Odd extents, thin volumes, and directions outside the range of the exact short division / add-a-constant rounding (zero, tiny,
+    huge, NaN, inf: the generic div.rn.f32 / cvt.rni path of the wavefront marcher)."""
+    ob, planes, trc, vol, t = _mk(vrt, oracle, shape, 17, volk, keep_i16=(volk == "i16"))
+    pos, d = S.random_rays(ob, 30000, seed=5, dir_kind="f32", scale=1.1)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x1234)
+    d[:200] = 0.0
+    d[200:400] *= np.float32(1e-30)
+    d[400:600] *= np.float32(1e25)
+    d[600:620] = np.float32(np.nan)
+    d[620:640, 1] = np.float32(np.inf)
+    want = oracle.trace(vol, ob, pos, d, [1.0, 1.0, 1.0], 300, round_mode=oracle.ROUND_DEVICE)
+    for isc in ([1.0, 1.0, 1.0], [3.0, 0.5, 1e-3]):
+        want = oracle.trace(vol, ob, pos, d, isc, 300, round_mode=oracle.ROUND_DEVICE)
+        for k in (3, 4):
+            t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, 2)
+            got = list(t.trace_rays_cu(pos, d, isc, 0, 300))
+            w = [x.copy() for x in want[:4]]
+            # NaN payloads are unspecified (x86 keeps an operand's payload, the GPU returns the canonical NaN)
+            gd = got[1].view(np.uint32).copy(); wd = w[1].view(np.uint32).copy()
+            gd[np.isnan(got[1])] = 0x7FC00000; wd[np.isnan(w[1])] = 0x7FC00000
+            got[1], w[1] = gd, wd
+            _assert_same(got, w, "wavefront odd extents k=%d isc=%s %s %s" % (k, isc, shape, volk))
+    t.close()
+
+
 def test_device_probe_picks_the_marcher_without_a_sync(vrt, oracle):
     """vrt_trace_device on a large volume: a probe KERNEL looks at the device-resident rays and gates the single-launch and the
     wavefront marcher; a shuffled batch runs the wavefront kernel (rounds > 0), a coherent bundle does not (rounds == 0); the

@@ -27,6 +27,14 @@ KEYS = {
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1_throughput_pct",
     "sm__cycles_elapsed.avg": "sm_cycles",
+    "l1tex__data_pipe_lsu_wavefronts.sum": "l1_data_pipe_lsu_wavefronts",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_lsu_wavefronts_pct_of_peak",
+    "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed": "l1_lsu_writeback_active_pct",
+    "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum": "l1_tag_stage_load_wavefronts",
+    "smsp__warps_eligible.avg.per_cycle_active": "eligible_warps_per_cycle",
+    "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_instruction",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_per_issue",
+    "smsp__average_warp_latency_per_inst_issued.ratio": "warp_latency_per_instruction_cycles",
 }
 
 
@@ -62,6 +70,8 @@ def main():
             d["l2_to_l1_bytes_per_ray_step"] = d.get("l2_read_sectors_from_l1", 0) * 32.0 / steps
             d["l1_sector_bytes_per_ray_step"] = d.get("l1_global_load_sectors", 0) * 32.0 / steps
             d["g_ray_steps_per_s_under_ncu"] = steps / d["duration"] / 1e9
+            if "l1_data_pipe_lsu_wavefronts" in d:
+                d["l1_data_pipe_wavefronts_per_ray_step"] = d["l1_data_pipe_lsu_wavefronts"] / steps
         out.append(d)
     print(json.dumps(out if len(out) > 1 else out[0], indent=1))
 

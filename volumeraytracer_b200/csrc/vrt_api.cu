@@ -105,7 +105,7 @@ struct vrt_scene
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: kStatSlots block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
-    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{32}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }

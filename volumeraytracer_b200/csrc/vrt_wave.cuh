@@ -20,7 +20,8 @@
 // This replaces round 1's region mode (a cub radix sort and a kernel launch per round, 14 launches + 13 sorts per trace) at the same
 // marching rate; what was tried on the way and measured slower is in DESIGN.md section 6 (a CTA per brick with CTA-wide compaction:
 // latency-bound; warp work items with CTA-shared batches for L1 affinity: no gain, the front of bricks in flight outgrows L2;
-// prefetch.global.L1 one step ahead: 95 -> 56 G ray-steps/s).
+// prefetch.global.L1 one step ahead: 95 -> 56 G ray-steps/s; bricks in Morton instead of row-major order: 91 -> 80; one 256-bit load
+// (LDG.E.ENL2.256) for the z-adjacent corner pair of a row where it is naturally aligned: 91 -> 67).
 //
 // The kernel can be GATED by a device flag written by coherence_probe_kernel, so that vrt_trace_device -- which cannot look at
 // device buffers without a synchronisation -- enqueues probe + single-launch marcher + this kernel and exactly one of the two
@@ -310,11 +311,21 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         dz = __fmaf_rn(invz, gz, dz);
                         unpack2(dxy, dx, dy);
                         const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                        const float ilen = __fdiv_rn(0x42000000p0f, dot);                                    // cu:346
-                        unpack2(mul2(mul2(pack2(invx, invy), dxy), pack2(ilen, ilen)), sx, sy);              // cu:347
-                        const uint32_t nx = px + (uint32_t)__float2int_rn(sx);
-                        const uint32_t ny = py + (uint32_t)__float2int_rn(sy);
-                        const uint32_t nz = pz + (uint32_t)__float2int_rn(__fmul_rn(__fmul_rn(invz, dz), ilen));
+                        // cu:346-347 with the two exact shortcuts of march3_kernel's fast loop (the short division sequence and the
+                        // add-a-constant rounding, each proven equal to div.rn.f32 / cvt.rni over the whole |dir|^2 range the host
+                        // puts into dot_lo / dot_span: vrt_selftest_division); outside that range the original instructions run
+                        const unsigned long long sdxy = mul2(pack2(invx, invy), dxy);
+                        const float sdz = __fmul_rn(invz, dz);
+                        float ilen = div_fast(dot);
+                        unpack2(mul2(sdxy, pack2(ilen, ilen)), sx, sy);
+                        uint32_t ax = rni_small(sx), ay = rni_small(sy), az = rni_small(__fmul_rn(sdz, ilen));
+                        if (!div_is_fast_in(dot, m.dot_lo, m.dot_span))
+                        {
+                            ilen = __fdiv_rn(0x42000000p0f, dot);                                            // cu:346
+                            unpack2(mul2(sdxy, pack2(ilen, ilen)), sx, sy);                                  // cu:347
+                            ax = (uint32_t)__float2int_rn(sx); ay = (uint32_t)__float2int_rn(sy); az = (uint32_t)__float2int_rn(__fmul_rn(sdz, ilen));
+                        }
+                        const uint32_t nx = px + ax, ny = py + ay, nz = pz + az;
                         moved = (px ^ nx) | (py ^ ny) | (pz ^ nz);
                         px = nx; py = ny; pz = nz;
                     }

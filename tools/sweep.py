@@ -120,13 +120,14 @@ def cfg_c5i(size=1024, nray=4096, iterations=2048):
 
 
 def cfg_c4(size=512, nrays=8 << 20, iterations=4096):
+    nrays = int(os.environ.get("SWEEP_C4_RAYS", nrays))          # a shard of the batch, as one GPU of a multi-GPU run sees it
     ior = W.solve_harmonic_torch(size, dev, inner_radius=64.0 * size / 512.0, sweeps=300)
     tr = W.clear_translucency_torch((size,) * 3, dev)
     sc = vrt.TraceRaysCu.from_ior((size,) * 3, ior, tr, bricked=BRICK, texture=TEX, paired=PAIR); torch.cuda.synchronize()
     pos, d = W.rays_random(nrays, 8.0, size - 9.0, 0x5EED0004)
     tpos = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); tdir = torch.from_numpy(d.reshape(-1)).to(dev)
     sc.normalise_rays_device(tpos, tdir)
-    run_variants("c4_%d" % size, sc, tpos, tdir, iterations, VARIANTS)
+    run_variants("c4_%d_%d" % (size, nrays), sc, tpos, tdir, iterations, VARIANTS)
     sc.close()
 
 

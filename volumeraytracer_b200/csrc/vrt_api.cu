@@ -1566,10 +1566,19 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     uint32_t *const flag_slots = (uint32_t *)t_ctx.h_stage;
     constexpr uint64_t kFlagSlots = ThreadCtx::kSmallBytes / 4;
 
-    uint64_t index = 0;
-    for (uint64_t off = 0; off < n && result == VRT_OK; off += chunk, ++index)
+    // The first chunk's H2D copy and the last chunk's D2H copy cannot overlap any marching: keep those two chunks small (one wave of
+    // the persistent grid) when the regular chunk is several waves (config 5 on one GPU: 16 chunks of 7 waves; head + tail 4.4 -> ~1 ms)
+    uint64_t edge = 0;
+    if (s->opt_chunk.load() == 0 && !want_path && region == 0 && s->dim == 3)
     {
-        const uint64_t m = std::min(chunk, n - off);
+        const uint64_t wave = std::max<uint64_t>(1u << 17, (uint64_t)s->num_sms * 1024);
+        if (chunk >= 2 * wave && n >= 4 * chunk) edge = wave;
+    }
+    uint64_t index = 0;
+    for (uint64_t off = 0, m = 0; off < n && result == VRT_OK; off += m, ++index)
+    {
+        m = std::min(chunk, n - off);
+        if (edge) m = off == 0 ? edge : (n - off <= chunk + edge ? (n - off > edge ? n - off - edge : n - off) : chunk);
         cudaStream_t q = t_ctx.st[index & 1];
         // one stream-ordered allocation per chunk: [pos | dir | eit | light | counter | path]
         Pending c;

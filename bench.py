@@ -260,7 +260,19 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
     peak = num_sms * 4 * sm_mhz * 1e6
     ach = warp_instr / launch_s
     warp_steps = cnt[2]
-    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-instr/s", "frac": ach / peak,
+    cost_model = None
+    bc = blocks.get("blocks_issue_cycles")
+    if bc:
+        model_cycles = sum(cnt[i] * bc[nm] for i, nm in enumerate(names)) + cnt[8] * bc.get("reload_partial", 1.0)
+        sched_cycles = launch_s * sm_mhz * 1e6 * num_sms * 4
+        cost_model = {"scheduler_cycles_additive_model": model_cycles, "scheduler_cycles_elapsed": sched_cycles, "model_over_elapsed": model_cycles / sched_cycles,
+                      "cycles_per_warp_step_model": model_cycles / max(warp_steps, 1), "cycles_per_warp_step_elapsed": sched_cycles / max(warp_steps, 1),
+                      "block_issue_cycles": bc,
+                      "what": "measured per-instruction scheduler cost on this GPU (tools/pipe_bench.cu, profiles/r02_pipe_bench.jsonl: scalar fp32 1.1 cycles, "
+                              "packed f32x2 2.0, logic/compare/permute/shift/IMAD 2.0, IADD3 1.0, mixes nearly additive) x the block issue counts of this run.  "
+                              "> 1 means the kernel already runs faster than the additive model allows (partial pipe overlap): `frac` below 1 is not headroom, "
+                              "half of the step loop's instructions cost two scheduler cycles each"}
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-instr/s", "frac": ach / peak, "issue_cost_model": cost_model,
             "traffic": None, "warp_instructions_per_pass": warp_instr, "warp_steps_per_pass": warp_steps,
             "warp_instructions_per_warp_step": warp_instr / max(warp_steps, 1),
             "lane_efficiency": cnt[7] / max(32 * warp_steps, 1), "reloads_per_warp_step": cnt[3] / max(warp_steps, 1),

@@ -145,18 +145,39 @@ def analyse(sass):
         "fast_step": n_fast_all - n_reload, "reload": n_reload, "reload_partial": 1, "mid": n_mid, "generic": n_rest - n_mid,
         "refill": n_refill, "retire": n_retire, "outer": max(n_outer, 0),
     }
+    cost_fast_all = sum(issue_cost(t) for _, t in fb)
+    cost_reload = sum(issue_cost(t) for _, t in body(*reload_r))
+    costs = {"fast_step": round(cost_fast_all - cost_reload, 2), "reload": round(cost_reload, 2), "reload_partial": 1.0}
+    for nm in ("mid", "generic", "refill", "retire", "outer"):
+        costs[nm] = round(counts[nm] * 1.4, 2)                 # not on the hot path: the kernel-wide average cost per instruction
     mix = {}
     for _, t in fb:
         op = re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0]
         mix[op] = mix.get(op, 0) + 1
     return {
-        "kernel": None, "instructions_total": len(ins), "blocks": counts,
+        "kernel": None, "instructions_total": len(ins), "blocks": counts, "blocks_issue_cycles": costs,
         "loops": {"outer": [hex(outer[0]), hex(outer[1])], "for": [hex(forl[0]), hex(forl[1])], "fast": [hex(fast[0]), hex(fast[1])],
                   "reload": [hex(reload_r[0]), hex(reload_r[1])]},
         "fast_loop_opcode_mix": dict(sorted(mix.items(), key=lambda kv: -kv[1])),
         "sass_sha1": hashlib.sha1(ops.encode()).hexdigest(),
         "stat_slots": {"outer": 0, "refill": 1, "fast_step": 2, "reload": 3, "mid": 4, "generic": 5, "retire": 6, "lane_steps": 7, "reload_partial": 8},
     }
+
+
+# Scheduler cycles per warp-instruction, measured with tools/pipe_bench.cu on a B200 at the marcher's occupancy (8 warps per scheduler;
+# profiles/r02_pipe_bench.jsonl): scalar fp32 ~1.1, packed fp32x2 2.0, logic / compare / permute / shift / IMAD 2.0, IADD3 1.0; a mix of two
+# kinds costs (nearly) the SUM of its parts (FFMA2+LOP3 4.0 per pair, FFMA+LOP3 2.76 instead of 3.15) -- the pipes hardly overlap.  Kinds
+# that were not measured (branches, loads, MOV, conversions, MUFU) are counted as 1.
+ISSUE_COST = [(r"^(FFMA2|FMUL2|FADD2)", 2.0), (r"^(FFMA|FADD|FMUL)\b", 1.1), (r"^(LOP3|ISETP|PRMT|SHF|SEL|PLOP3|VIMNMX|IMNMX|LEA|FSETP|FMNMX|POPC|FLO)", 2.0),
+              (r"^IMAD", 2.0), (r"^(IADD3|VIADD|IADD)", 1.0)]
+
+
+def issue_cost(text):
+    op = re.sub(r"^@!?U?P\d+\s+", "", text)
+    for pat, c in ISSUE_COST:
+        if re.search(pat, op):
+            return c
+    return 1.0
 
 
 def main():

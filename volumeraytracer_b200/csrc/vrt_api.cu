@@ -1269,7 +1269,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
         if (lo == lo && lo < 0x1p97f) { if (lo < 0x1p-95f) lo = 0x1p-95f; memcpy(&lo_bits, &lo, 4); }
         p.dot_lo = lo_bits; p.dot_span = 0x70000000u - lo_bits;
     }
-    p.one[0] = p.one[1] = 1.0f;
+    p.one[0] = p.one[1] = 1.0f; p.zero = 0;
     p.refill = counter ? (int)s->opt_refill.load() : 0;
     p.counter = counter;
     p.cap_flag = scratch ? (uint32_t *)(scratch + 1) : nullptr;

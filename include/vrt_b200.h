@@ -110,9 +110,6 @@ enum {
     VRT_OPT_WAVE_TAIL_PERMILLE = 11, /* when at most this share of the batch is still alive, the rest is marched without bricks (default 20) */
     VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = occupancy limit) */
     VRT_OPT_WAVE_REFILL   = 14, /* a warp takes new rays from the brick-sorted list when at least this many lanes are idle (default 8) */
-    VRT_OPT_WAVE_STAGED   = 16, /* 1: the wavefront marcher stages every brick in SHARED MEMORY (csrc/vrt_wave.cuh, STAGED variant: bricks of at most 2^4 cells
-                                   per axis, no margin; corner fetches become shared-memory loads); 0: bricks are read through L1/L2 */
-    VRT_OPT_WAVE_SMAX     = 17, /* staged variant: steps a ray may take per round before it is suspended where it is (default 64) */
     VRT_INFO_WAVE_ROUNDS  = 102, /* read-only: rounds the last wavefront launch on this scene took (synchronises) */
     VRT_OPT_REGION_ROUNDS = 7,  /* accepted for compatibility, unused (the wavefront marcher runs as many rounds as the batch needs) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive

@@ -333,14 +333,6 @@ def test_wavefront_mode_is_bit_identical(vrt, oracle, volk, dirk, live):
         got = t.trace_rays_cu(pos, d, isc, minb, 700, live_translucency=live)
         _assert_same(got, want[:4], "wavefront k=%d margin=%d check=%d tail=%d %s/%s" % (k, margin, check, tail, volk, dirk))
         assert t.get_option(vrt.VRT_INFO_WAVE_ROUNDS) >= 1
-    # STAGED variant: bricks marched out of shared memory, rays suspended after `smax` steps per round
-    for k, smax, tail in ((3, 64, 20), (4, 64, 20), (4, 7, 0), (3, 1000, 500), (4, 1, 1000), (5, 33, 20)):
-        t.set_option(vrt.VRT_OPT_WAVE_STAGED, 1); t.set_option(vrt.VRT_OPT_WAVE_LOG2, k)
-        t.set_option(vrt.VRT_OPT_WAVE_SMAX, smax); t.set_option(vrt.VRT_OPT_WAVE_TAIL_PERMILLE, tail)
-        got = t.trace_rays_cu(pos, d, isc, minb, 700, live_translucency=live)
-        _assert_same(got, want[:4], "staged wavefront k=%d smax=%d tail=%d %s/%s" % (k, smax, tail, volk, dirk))
-        assert t.get_option(vrt.VRT_INFO_WAVE_ROUNDS) >= 1
-    t.set_option(vrt.VRT_OPT_WAVE_STAGED, 0); t.set_option(vrt.VRT_OPT_WAVE_TAIL_PERMILLE, 20)
     # the cap: every ray that is still inside after `iterations` steps reports `iterations`, and the flag says so
     t.set_option(vrt.VRT_OPT_WAVE_LOG2, 3); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, 2); t.set_option(vrt.VRT_OPT_WAVE_CHECK, 16)
     want5 = oracle.trace(vol, ob, pos, d, isc, 5, translucency=trc if live else None, min_brightness=minb, round_mode=oracle.ROUND_DEVICE)
@@ -366,15 +358,15 @@ def test_wavefront_odd_extents_and_extreme_directions(vrt, oracle, shape, volk):
     want = oracle.trace(vol, ob, pos, d, [1.0, 1.0, 1.0], 300, round_mode=oracle.ROUND_DEVICE)
     for isc in ([1.0, 1.0, 1.0], [3.0, 0.5, 1e-3]):
         want = oracle.trace(vol, ob, pos, d, isc, 300, round_mode=oracle.ROUND_DEVICE)
-        for k, staged in ((3, 0), (4, 0), (3, 1), (4, 1)):
-            t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, 2); t.set_option(vrt.VRT_OPT_WAVE_STAGED, staged)
+        for k in (3, 4):
+            t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, 2)
             got = list(t.trace_rays_cu(pos, d, isc, 0, 300))
             w = [x.copy() for x in want[:4]]
             # NaN payloads are unspecified (x86 keeps an operand's payload, the GPU returns the canonical NaN)
             gd = got[1].view(np.uint32).copy(); wd = w[1].view(np.uint32).copy()
             gd[np.isnan(got[1])] = 0x7FC00000; wd[np.isnan(w[1])] = 0x7FC00000
             got[1], w[1] = gd, wd
-            _assert_same(got, w, "wavefront odd extents k=%d staged=%d isc=%s %s %s" % (k, staged, isc, shape, volk))
+            _assert_same(got, w, "wavefront odd extents k=%d isc=%s %s %s" % (k, isc, shape, volk))
     t.close()
 
 

@@ -105,7 +105,7 @@ struct vrt_scene
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: kStatSlots block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
-    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8}, opt_wave_staged{0}, opt_wave_smax{64};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -668,8 +668,6 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_WAVE_TAIL_PERMILLE: if (v < 0 || v > 1000) return fail(VRT_ERR_INVALID, "wavefront tail must be 0..1000 permille"); s->opt_wave_tail = v; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: if (v < 0 || v > 8) return fail(VRT_ERR_INVALID, "wavefront CTAs per SM must be 0..8"); s->opt_wave_ctas = v; break;
     case VRT_OPT_WAVE_REFILL:    if (v < 1 || v > 32) return fail(VRT_ERR_INVALID, "wavefront refill threshold must be 1..32"); s->opt_wave_refill = v; break;
-    case VRT_OPT_WAVE_STAGED:    if (v < 0 || v > 1) return fail(VRT_ERR_INVALID, "wavefront staging must be 0 or 1"); s->opt_wave_staged = v; break;
-    case VRT_OPT_WAVE_SMAX:      if (v < 1 || v > 65536) return fail(VRT_ERR_INVALID, "wavefront steps per round must be 1..65536"); s->opt_wave_smax = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -694,8 +692,6 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_WAVE_TAIL_PERMILLE: *v = s->opt_wave_tail; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: *v = s->opt_wave_ctas; break;
     case VRT_OPT_WAVE_REFILL: *v = s->opt_wave_refill; break;
-    case VRT_OPT_WAVE_STAGED: *v = s->opt_wave_staged; break;
-    case VRT_OPT_WAVE_SMAX: *v = s->opt_wave_smax; break;
     case VRT_INFO_WAVE_ROUNDS: *v = s->last_wave_rounds_host(); break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
@@ -736,7 +732,7 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
     s->opt_wave = src->opt_wave.load(); s->opt_wave_margin = src->opt_wave_margin.load(); s->opt_wave_check = src->opt_wave_check.load();
     s->opt_wave_tail = src->opt_wave_tail.load(); s->opt_wave_ctas = src->opt_wave_ctas.load();
-    s->opt_wave_refill = src->opt_wave_refill.load(); s->opt_wave_staged = src->opt_wave_staged.load(); s->opt_wave_smax = src->opt_wave_smax.load();
+    s->opt_wave_refill = src->opt_wave_refill.load();
     *out = s;
     return VRT_OK;
 }
@@ -1138,23 +1134,15 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
 }
 
 // ---- wavefront mode (vrt_wave.cuh): ONE cooperative launch does bucket passes + marching, round by round -------------------
-// bytes of dynamic shared memory of the STAGED variant: the brick's (E+1)^3 voxels
-static size_t wave_box_bytes(const vrt_scene *s, int k) { const size_t e1 = ((size_t)1 << k) + 1; return e1 * e1 * e1 * 4 * elem_size(s->store); }
-
-template <typename VoxT, bool DIR_I16, bool LIVE, bool STAGED>
+template <typename VoxT, bool DIR_I16, bool LIVE>
 static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
 {
-    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE, STAGED>;
-    const size_t smem = STAGED ? wave_box_bytes(s, wp.log2_brick) : 0;
-    static std::atomic<unsigned long long> carved{0};  // per device.  Global-memory variant: next to no shared memory in use, give the unified array to L1
+    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE>;
+    static std::atomic<unsigned long long> carved{0};  // per device: next to no shared memory in use, give the unified array to L1
     const unsigned long long bit = 1ull << (s->device & 63);
-    if (!(carved.fetch_or(bit) & bit))
-    {
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, STAGED ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutMaxL1);
-        if (STAGED) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    }
+    if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, 0);
     if (e != cudaSuccess) return e;
     const int cap = (int)s->opt_wave_ctas.load();
     if (cap > 0 && cap < per_sm) per_sm = cap;
@@ -1162,17 +1150,7 @@ static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t 
     const unsigned grid = (unsigned)(per_sm * s->num_sms);          // cooperative: every CTA must be resident
     void *args[] = {(void *)&wp};
     ++g_launches;
-    return cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kWaveThreads), args, smem, st);
-}
-
-template <typename VoxT>
-static cudaError_t launch_wave_vox(const vrt_scene *s, WaveParams &wp, bool di16, bool live, bool staged, cudaStream_t st)
-{
-    if (staged)
-        return di16 ? (live ? launch_wave<VoxT, true, true, true>(s, wp, st) : launch_wave<VoxT, true, false, true>(s, wp, st))
-                    : (live ? launch_wave<VoxT, false, true, true>(s, wp, st) : launch_wave<VoxT, false, false, true>(s, wp, st));
-    return di16 ? (live ? launch_wave<VoxT, true, true, false>(s, wp, st) : launch_wave<VoxT, true, false, false>(s, wp, st))
-                : (live ? launch_wave<VoxT, false, true, false>(s, wp, st) : launch_wave<VoxT, false, false, false>(s, wp, st));
+    return cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kWaveThreads), args, 0, st);
 }
 
 static bool wave_geometry(const vrt_scene *s, int k, uint32_t nb[3], uint64_t *K)
@@ -1188,15 +1166,6 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
 {
     const uint64_t n = mp.n;
     uint32_t nb[3]; uint64_t K = 0;
-    // STAGED variant (bricks marched out of shared memory): the brick must fit shared memory twice per SM -- 2^4 cells per axis for a
-    // float scene (17^3 x 16 B = 79 KB) -- and the finer brick grid must fit the histogram; otherwise the global-memory variant runs
-    bool staged = s->opt_wave_staged.load() != 0;
-    if (staged)
-    {
-        int ks = std::min(k, 4);
-        while (ks >= 3 && wave_box_bytes(s, ks) > 100 * 1024) --ks;
-        if (ks >= 3 && wave_geometry(s, ks, nb, &K)) k = ks; else staged = false;
-    }
     if (!wave_geometry(s, k, nb, &K)) return fail(VRT_ERR_INVALID, "too many bricks: raise VRT_OPT_WAVE_LOG2");
     if (n >= (1ull << 31)) return fail(VRT_ERR_INVALID, "wavefront mode takes at most 2^31-1 rays per call");
     int coop = 0;
@@ -1205,8 +1174,7 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_pos = 0, o_dir = o_pos + al(n * 12), o_it = o_dir + al(n * 12), o_light = o_it + al(n * 4), o_key = o_light + al(n * 4);
     const size_t o_o0 = o_key + al(n * 4), o_o1 = o_o0 + al(n * 4), o_h0 = o_o1 + al(n * 4), o_h1 = o_h0 + al(K * 4), o_off = o_h1 + al(K * 4);
-    const size_t o_part = o_off + al((K + 1) * 4), o_ctl = o_part + al(4096 * 4);
-    const size_t o_nz = o_ctl + 256, o_pnz = o_nz + al(staged ? K * 4 : 0), total = o_pnz + al(staged ? 4096 * 4 : 0);
+    const size_t o_part = o_off + al((K + 1) * 4), o_ctl = o_part + al(4096 * 4), total = o_ctl + 256;
     char *ws = nullptr;
     VRT_CUDA(pool_alloc((void **)&ws, total, s->device, st));
     WaveParams wp;
@@ -1225,12 +1193,16 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
     wp.steps_per_check = (int)s->opt_wave_check.load();
     wp.refill = (uint32_t)s->opt_wave_refill.load();
     wp.max_rounds = mp.iterations + 8u < mp.iterations ? 0xFFFFFFFFu : mp.iterations + 8u;
-    wp.nz_list = (uint32_t *)(ws + o_nz); wp.partial_nz = (uint32_t *)(ws + o_pnz);
-    wp.smax = (uint32_t)s->opt_wave_smax.load();
-    if (staged) wp.margin = 0;                                       // a staged brick is exactly its cells
     cudaError_t err = cudaMemsetAsync(wp.ctl, 0, 256, st);
     if (err == cudaSuccess)
-        err = s->store == VRT_F32 ? launch_wave_vox<float>(s, wp, di16, live, staged, st) : launch_wave_vox<int16_t>(s, wp, di16, live, staged, st);
+    {
+        if (s->store == VRT_F32)
+            err = di16 ? (live ? launch_wave<float, true, true>(s, wp, st) : launch_wave<float, true, false>(s, wp, st))
+                       : (live ? launch_wave<float, false, true>(s, wp, st) : launch_wave<float, false, false>(s, wp, st));
+        else
+            err = di16 ? (live ? launch_wave<int16_t, true, true>(s, wp, st) : launch_wave<int16_t, true, false>(s, wp, st))
+                       : (live ? launch_wave<int16_t, false, true>(s, wp, st) : launch_wave<int16_t, false, false>(s, wp, st));
+    }
     if (err == cudaSuccess)
     {
         if (!s->d_wave_info && cudaMalloc((void **)&s->d_wave_info, kCtlWords * 4) != cudaSuccess) { cudaGetLastError(); s->d_wave_info = nullptr; }

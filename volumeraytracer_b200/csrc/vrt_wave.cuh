@@ -44,7 +44,7 @@ constexpr uint32_t kWaveDone = 0xFFFFFFFFu;
 constexpr int      kWaveThreads = 256;           // threads per CTA
 
 // control block (device): written by the scan phase, read by everybody after the grid barrier
-enum { kCtlAlive = 0, kCtlItems = 1, kCtlCursor = 2, kCtlTail = 3, kCtlPrevCount = 4, kCtlRounds = 5, kCtlWords = 8 };
+enum { kCtlAlive = 0, kCtlCursor = 2, kCtlTail = 3, kCtlPrevCount = 4, kCtlRounds = 5, kCtlWords = 8 };
 
 struct WaveParams
 {
@@ -66,11 +66,6 @@ struct WaveParams
     uint32_t   refill;           // a warp takes new rays from the list when at least this many lanes are idle
     int        steps_per_check;  // marching steps between two refill polls
     uint32_t   max_rounds;       // safety net (a round always advances every ray by at least one step)
-    // STAGED variant (march3_wave_kernel<..., true>): the bricks that hold rays this round, in key order, and how many steps a ray may
-    // take per round
-    uint32_t  *nz_list;          // [K]
-    uint32_t  *partial_nz;       // [gridDim] per-CTA counts of non-empty bricks of the scan
-    uint32_t   smax;
 };
 
 __device__ __forceinline__ uint32_t wave_key(uint32_t px, uint32_t py, uint32_t pz, const WaveParams &p)
@@ -136,16 +131,8 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t &total, uint
     return before + inc - v;
 }
 
-// STAGED = true: the march phase of a round works brick by brick out of SHARED MEMORY.  A CTA takes a brick that holds rays (from the
-// compact list the scan builds), copies the brick's (E+1)^3 voxels -- E = 2^log2_brick cells per axis plus the far corners -- into shared
-// memory with coalesced row loads, and its warps then pull the brick's rays 32 at a time and march each until it leaves the brick, has
-// finished, or has taken `smax` steps (it is then suspended where it is and continues in the next round).  Every corner fetch of the
-// march is a shared-memory load: the L1 data pipe, which delivers one 128-byte line per cycle to the scattered global gathers of the
-// other variant (its bound: 77 % of that peak on config 4), serves a warp's random 16-byte shared loads several lanes per cycle, and
-// a brick is read from L2/DRAM once per round as full rows.  Same arithmetic, same bits.  The last (tail) round has no boxes and runs
-// the global-memory code.  Dynamic shared memory: (E+1)^3 voxels.
-template <typename VoxT, bool DIR_I16, bool LIVE, bool STAGED = false>
-__global__ void __launch_bounds__(kWaveThreads, STAGED ? 2 : VRT_WAVE_MINCTAS) march3_wave_kernel(const WaveParams p)
+template <typename VoxT, bool DIR_I16, bool LIVE>
+__global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_kernel(const WaveParams p)
 {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const MarchParams &m = p.m;
@@ -155,8 +142,7 @@ __global__ void __launch_bounds__(kWaveThreads, STAGED ? 2 : VRT_WAVE_MINCTAS) m
     const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + tid, gsize = (unsigned long long)gridDim.x * blockDim.x;
 
     __shared__ uint32_t s_scan[kWaveThreads / 32];
-    __shared__ uint32_t s_item, s_cursor;                 // STAGED: the brick list entry the CTA works on, the next ray of that brick
-    extern __shared__ uint4 s_box[];                      // STAGED: the brick's voxels, [(E+1)][(E+1)][(E+1)]
+    __shared__ uint32_t s_base;
 
     // ---- phase 0: every ray into the state arrays, first histogram ---------------------------------------------------------
     for (unsigned long long i = gtid; i < (unsigned long long)p.K; i += gsize) { p.hist[0][i] = 0; p.hist[1][i] = 0; }
@@ -184,41 +170,30 @@ __global__ void __launch_bounds__(kWaveThreads, STAGED ? 2 : VRT_WAVE_MINCTAS) m
         const uint32_t slice = ((p.K + gridDim.x - 1) / gridDim.x + kWaveThreads - 1) / kWaveThreads * kWaveThreads;
         const uint32_t b_lo = min(p.K, blockIdx.x * slice), b_hi = min(p.K, b_lo + slice);
         {
-            uint32_t a = 0, nz = 0, total;
-            for (uint32_t k = b_lo + tid; k < b_hi; k += kWaveThreads) { const uint32_t c = p.hist[cur][k]; a += c; nz += c ? 1u : 0u; }
+            uint32_t a = 0, total;
+            for (uint32_t k = b_lo + tid; k < b_hi; k += kWaveThreads) a += p.hist[cur][k];
             block_scan(a, total, s_scan);
             if (tid == 0) p.partial[blockIdx.x] = total;
-            if (STAGED)
-            {
-                block_scan(nz, total, s_scan);
-                if (tid == 0) p.partial_nz[blockIdx.x] = total;
-            }
         }
         grid.sync();
         // ---- bucket pass 1b: every brick's first slot in order[] (its scatter cursor), control block -----------------------------
         {
-            uint32_t a = 0, before, all = 0, a_nz = 0, before_nz = 0, all_nz = 0;
-            for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads)
-            {
-                const uint32_t v = p.partial[c]; if (c < blockIdx.x) a += v; all += v;
-                if (STAGED) { const uint32_t w = p.partial_nz[c]; if (c < blockIdx.x) a_nz += w; all_nz += w; }
-            }
+            uint32_t a = 0, before, all = 0;
+            for (uint32_t c = tid; c < gridDim.x; c += kWaveThreads) { const uint32_t v = p.partial[c]; if (c < blockIdx.x) a += v; all += v; }
             block_scan(a, before, s_scan);                             // rays in the slices before this CTA's
-            if (STAGED) block_scan(a_nz, before_nz, s_scan);           // bricks with rays in the slices before this CTA's
             if (blockIdx.x == 0)
             {
-                uint32_t alive, items = 0;
+                uint32_t alive;
                 block_scan(all, alive, s_scan);
-                if (STAGED) block_scan(all_nz, items, s_scan);
                 if (tid == 0)
                 {
                     p.bin_off[p.K] = 0;                                // the tail round's single cursor
-                    p.ctl[kCtlAlive] = alive; p.ctl[kCtlCursor] = 0; p.ctl[kCtlItems] = items;
+                    p.ctl[kCtlAlive] = alive; p.ctl[kCtlCursor] = 0;
                     p.ctl[kCtlTail] = alive <= p.tail_rays ? 1u : 0u;
                     p.ctl[kCtlRounds] = round + 1;
                 }
             }
-            uint32_t off = before, off_nz = before_nz;
+            uint32_t off = before;
             for (uint32_t k0 = b_lo; k0 < b_hi; k0 += kWaveThreads)
             {
                 const uint32_t k = k0 + tid;
@@ -231,13 +206,6 @@ __global__ void __launch_bounds__(kWaveThreads, STAGED ? 2 : VRT_WAVE_MINCTAS) m
                     p.hist[cur ^ 1][k] = 0;                            // the next round's histogram starts empty
                 }
                 off += tile_total;
-                if (STAGED)
-                {
-                    uint32_t tile_nz;
-                    const uint32_t ex_nz = block_scan(c ? 1u : 0u, tile_nz, s_scan);
-                    if (c) p.nz_list[off_nz + ex_nz] = k;
-                    off_nz += tile_nz;
-                }
             }
         }
         grid.sync();
@@ -258,161 +226,6 @@ __global__ void __launch_bounds__(kWaveThreads, STAGED ? 2 : VRT_WAVE_MINCTAS) m
         // round and then served by L2 (and L1).  A ray marches inside its brick's box (the box is per lane); idle lanes are refilled
         // from the list as soon as `refill` of them are free, so warps stay full although rays leave their bricks after very
         // different numbers of steps.
-        if (STAGED && !tail)
-        {
-            const float invx = m.invx, invy = m.invy, invz = m.invz;
-            const uint32_t n_items = p.ctl[kCtlItems];
-            const uint32_t E = 1u << p.log2_brick, E1 = E + 1u;
-            const unsigned warp = tid >> 5;
-            uint32_t next_item = 0;
-            if (tid == 0) next_item = atomicAdd(&p.ctl[kCtlCursor], 1u);
-            for (;;)
-            {
-                __syncthreads();                                     // every warp is done with the previous brick (its box, its cursor)
-                if (tid == 0) { s_item = next_item; s_cursor = 0; }
-                __syncthreads();
-                const uint32_t item = s_item;
-                if (item >= n_items) break;                          // uniform over the CTA
-                const uint32_t brick = p.nz_list[item];
-                const uint32_t cnt = p.hist[cur][brick], first = p.bin_off[brick] - cnt;   // the scatter pass left the cursor at the end of the brick's slots
-                const uint32_t bx = brick / (p.nby * p.nbz), brem = brick - bx * (p.nby * p.nbz), by_ = brem / p.nbz, bz_ = brem - by_ * p.nbz;
-                const uint32_t ox = bx * E, oy = by_ * E, oz = bz_ * E;                    // first voxel of the brick
-                // ---- stage the brick: rows of E+1 voxels along z, one row per warp pass (coalesced), voxels beyond the volume skipped
-                // (no ray reads them: a cell at or beyond bounds-1 is outside, cu:335)
-                {
-                    // asynchronous copies (LDGSTS): all of a thread's rows are in flight at once, nothing passes through registers
-                    const uint32_t vx = m.limx + 1u, vy = m.limy + 1u, vz = m.limz + 1u;   // voxels per axis (lim = bounds - 1)
-                    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_box);
-                    for (uint32_t r = warp; r < E1 * E1; r += kWaveThreads / 32)
-                    {
-                        const uint32_t x = r / E1, y = r - x * E1;
-                        if (lane < E1 && ox + x < vx && oy + y < vy && oz + lane < vz)
-                        {
-                            const uint32_t cell = ((ox + x) * m.by + (oy + y)) * m.bz + (oz + lane);       // cu:113
-                            if (sizeof(VoxT) == 4)
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + (r * E1 + lane) * 16u), "l"((const char *)m.volume + (size_t)cell * 16u) : "memory");
-                            else
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sbase + (r * E1 + lane) * 8u), "l"((const char *)m.volume + (size_t)cell * 8u) : "memory");
-                        }
-                    }
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                }
-                if (tid == 0) next_item = atomicAdd(&p.ctl[kCtlCursor], 1u);               // fetched while this brick is marched
-                __syncthreads();
-                // the brick's box in 16.16: cells [o, o + E) clipped to the volume
-                const uint32_t lo_x = ox << 16, lo_y = oy << 16, lo_z = oz << 16;
-                const uint32_t sp_x = (min(ox + E, m.limx) - ox) << 16, sp_y = (min(oy + E, m.limy) - oy) << 16, sp_z = (min(oz + E, m.limz) - oz) << 16;
-                for (;;)
-                {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cursor, 32u);
-                    base = __shfl_sync(FULL, base, 0);
-                    if (base >= cnt) break;                          // uniform over the warp
-                    if (base + lane >= cnt) continue;                // (the warp's next grab fails: these lanes just wait there)
-                    const uint32_t ray = p.order[cur][first + base + lane];
-                    uint32_t px = p.st_pos[(size_t)ray * 3], py = p.st_pos[(size_t)ray * 3 + 1], pz = p.st_pos[(size_t)ray * 3 + 2];
-                    float dx = p.st_dir[(size_t)ray * 3], dy = p.st_dir[(size_t)ray * 3 + 1], dz = p.st_dir[(size_t)ray * 3 + 2];
-                    uint32_t it = p.st_it[ray], brightness = LIVE ? p.st_light[ray] : 0xFFFFFFFFu, cached_tr = 0, moved = 0xFFFFFFFFu;
-                    const uint32_t it_stop = it - min(it, p.smax);
-                    bool done = false;
-                    uint32_t it_final = 0, clear = 0, v0 = 0;
-                    CornersZ cz;                                     // the fast loop's cell cache (vrt_march.cuh): {d0,d1} per corner, channel 2 in z pairs
-                    while (it != it_stop)
-                    {
-                        if (!(((px - lo_x) < sp_x) & ((py - lo_y) < sp_y) & ((pz - lo_z) < sp_z)))
-                        {
-                            // outside the brick: outside the volume as well (the reference's loop condition fails, cu:335)?
-                            if (!((px < m.limx16) & (py < m.limy16) & (pz < m.limz16))) { done = true; it_final = it; }
-                            break;
-                        }
-                        --it;
-                        if (moved >= 0x10000u)
-                        {
-                            const uint32_t cx = (px >> 16) - ox, cy = (py >> 16) - oy, cz_ = (pz >> 16) - oz;
-                            v0 = (cx * E1 + cy) * E1 + cz_;
-                            const uint32_t v1 = v0 + E1, v2 = v0 + E1 * E1, v3 = v2 + E1;
-                            if (LIVE) cached_tr = ldg_nc_u32(m.translucency + (((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16)));
-                            Corners t;
-                            if (sizeof(VoxT) == 4)
-                            {
-                                const float4 *sb = (const float4 *)s_box;
-                                t.c[0][0] = sb[v0]; t.c[0][1] = sb[v0 + 1]; t.c[1][0] = sb[v1]; t.c[1][1] = sb[v1 + 1];
-                                t.c[2][0] = sb[v2]; t.c[2][1] = sb[v2 + 1]; t.c[3][0] = sb[v3]; t.c[3][1] = sb[v3 + 1];
-                            }
-                            else
-                            {
-                                const int2 *sb = (const int2 *)s_box;
-                                t.c[0][0] = short4_to_float4(sb[v0]); t.c[0][1] = short4_to_float4(sb[v0 + 1]); t.c[1][0] = short4_to_float4(sb[v1]); t.c[1][1] = short4_to_float4(sb[v1 + 1]);
-                                t.c[2][0] = short4_to_float4(sb[v2]); t.c[2][1] = short4_to_float4(sb[v2 + 1]); t.c[3][0] = short4_to_float4(sb[v3]); t.c[3][1] = short4_to_float4(sb[v3 + 1]);
-                            }
-                            clear = corners_to_z(cz, t, sizeof(VoxT) == 4 ? m.zero : 0u);
-                        }
-                        if (LIVE)                                                                            // cu:337-341
-                        {
-                            const uint32_t absorb = 0xFFFFFFFFu - cached_tr;
-                            brightness -= min(brightness, absorb);
-                            if (brightness < m.min_brightness) { done = true; it_final = it + 1u; break; }
-                        }
-                        if ((int32_t)clear >= 0)
-                        {
-                            // a corner of the cell may be opaque: channel 3 of the sample (cu:342-343) from the staged voxels
-                            const uint32_t vv[4] = {v0, v0 + E1, v0 + E1 * E1, v0 + E1 * E1 + E1};
-                            float e[4][2];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                                for (int k = 0; k < 2; ++k)
-                                    e[r][k] = sizeof(VoxT) == 4 ? ((const float *)s_box)[(size_t)(vv[r] + k) * 4 + 3] : (float)((const short *)s_box)[(size_t)(vv[r] + k) * 4 + 3];
-                            float xl, xr, yl, yr, zl, zr;
-                            axis_weights(px, xl, xr); axis_weights(py, yl, yr); axis_weights(pz, zl, zr);
-                            const float a00 = __fmaf_rn(e[0][0], xl, __fmul_rn(e[2][0], xr)), a01 = __fmaf_rn(e[0][1], xl, __fmul_rn(e[2][1], xr));
-                            const float a10 = __fmaf_rn(e[1][0], xl, __fmul_rn(e[3][0], xr)), a11 = __fmaf_rn(e[1][1], xl, __fmul_rn(e[3][1], xr));
-                            const float b0 = __fmaf_rn(a00, yl, __fmul_rn(a10, yr)), b1 = __fmaf_rn(a01, yl, __fmul_rn(a11, yr));
-                            const float gw = __fmul_rn(__fmaf_rn(b0, zl, __fmul_rn(b1, zr)), 1.0f / 0x1000000000000p0f);
-                            if (gw > 0.0f) { done = true; it_final = it + 1u; break; }                       // cu:343
-                        }
-                        unsigned long long gxy;
-                        float gz, sx, sy;
-                        trilerp_z(cz, px, py, pz, gxy, gz, scale48_const());                                 // cu:342, channels 0..2
-                        const unsigned long long dxy = fma2(pack2(invx, invy), gxy, pack2(dx, dy));          // cu:344-345
-                        dz = __fmaf_rn(invz, gz, dz);
-                        unpack2(dxy, dx, dy);
-                        const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                        const unsigned long long sdxy = mul2(pack2(invx, invy), dxy);                        // cu:346-347, as in the other variant
-                        const float sdz = __fmul_rn(invz, dz);
-                        float ilen = div_fast(dot);
-                        unpack2(mul2(sdxy, pack2(ilen, ilen)), sx, sy);
-                        uint32_t ax = rni_small(sx), ay = rni_small(sy), az = rni_small(__fmul_rn(sdz, ilen));
-                        if (!div_is_fast_in(dot, m.dot_lo, m.dot_span))
-                        {
-                            ilen = __fdiv_rn(0x42000000p0f, dot);
-                            unpack2(mul2(sdxy, pack2(ilen, ilen)), sx, sy);
-                            ax = (uint32_t)__float2int_rn(sx); ay = (uint32_t)__float2int_rn(sy); az = (uint32_t)__float2int_rn(__fmul_rn(sdz, ilen));
-                        }
-                        const uint32_t nx = px + ax, ny = py + ay, nz = pz + az;
-                        moved = (px ^ nx) | (py ^ ny) | (pz ^ nz);
-                        px = nx; py = ny; pz = nz;
-                    }
-                    if (!done && it == 0u) { done = true; it_final = 0u; }                                   // cap (cu:335,350)
-                    if (done)
-                    {
-                        store_ray<DIR_I16, LIVE, false>(m, ray, px, py, pz, dx, dy, dz, it_final, brightness);
-                        p.key_of_ray[ray] = kWaveDone;
-                    }
-                    else                                                                                     // left the brick, or smax steps taken: next round
-                    {
-                        p.st_pos[(size_t)ray * 3] = px; p.st_pos[(size_t)ray * 3 + 1] = py; p.st_pos[(size_t)ray * 3 + 2] = pz;
-                        p.st_dir[(size_t)ray * 3] = dx; p.st_dir[(size_t)ray * 3 + 1] = dy; p.st_dir[(size_t)ray * 3 + 2] = dz;
-                        p.st_it[ray] = it;
-                        if (LIVE) p.st_light[ray] = brightness;
-                        const uint32_t key = wave_key(px, py, pz, p);
-                        p.key_of_ray[ray] = key;
-                        atomicAdd(&p.hist[cur ^ 1][key], 1u);
-                    }
-                }
-            }
-        }
-        else
         {
             const float invx = m.invx, invy = m.invy, invz = m.invz;
             uint32_t lo_x = 0, lo_y = 0, lo_z = 0, sp_x = 0, sp_y = 0, sp_z = 0;       // this lane's box: [lo, lo + span) in 16.16, clipped to the volume

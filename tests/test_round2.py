@@ -313,6 +313,31 @@ def test_normalise_accepts_rays_in_the_last_half_voxel(vrt, oracle, kind):
     sc.close()
 
 
+def test_host_call_chunk_schedule_on_a_large_batch(vrt, oracle):
+    """vrt_trace cuts a large batch into whole waves of the persistent grid with a small first and last chunk (head and tail of the
+    copy pipeline).  5 M + 17 rays is past the point where that schedule starts: every ray must come back, in place, with the bits
+    of the device-resident call and of the oracle."""
+    import torch
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (40, 36, 44), 23, "f32")
+    n = 5_000_017
+    pos, d = S.random_rays(ob, 4096, seed=3, dir_kind="f32", scale=1.1)
+    reps = -(-n // pos.shape[0])
+    pos = np.ascontiguousarray(np.tile(pos - np.uint32(0x10000) + np.uint32(0x777), (reps, 1))[:n])
+    d = np.ascontiguousarray(np.tile(d, (reps, 1))[:n])
+    pos[:, 2] += (np.arange(n, dtype=np.uint32) % np.uint32(977))            # not a periodic batch: a misplaced chunk would show
+    isc = [1.0, 1.0, 1.0]
+    dev = torch.device("cuda", 0)
+    tp = torch.from_numpy(pos.view(np.int32).reshape(-1)).to(dev); td = torch.from_numpy(d.reshape(-1)).to(dev)
+    want = [o.cpu().numpy() for o in t.trace_device(tp, td, isc, 0, 40)]
+    hp = pos.reshape(-1).copy(); hd = d.reshape(-1).copy(); hi = np.empty(n, np.uint32); hl = np.empty(n, np.uint32)
+    t.trace_host_buffers(hp, hd, isc, 0, 40, hp, hd, hi, hl)                 # in place, pageable
+    assert EQ(hp, want[0].view(np.uint32)) and EQ(hd, want[1]) and EQ(hi, want[2].view(np.uint32))
+    sel = np.arange(0, n, 997)
+    ref = oracle.trace(vol, ob, pos[sel], d[sel], isc, 40, round_mode=oracle.ROUND_DEVICE)
+    assert EQ(hp.reshape(-1, 3)[sel], ref[0]) and EQ(hi[sel], ref[2])
+    t.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # wavefront marcher (incoherent batches) and the device-side coherence probe
 

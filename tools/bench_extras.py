@@ -136,12 +136,39 @@ def run_config(name, dev, with_ref_cuda=False, host_call=True):
     return res
 
 
+def _c4_roofline(res, dev):
+    """Config 4 is bound by the L1 data pipe: on incoherent rays every lane of a corner load touches its own 128-byte line and the pipe
+    delivers one line (wavefront) per cycle and SM.  Wavefronts per ray-step come from the committed ncu capture of the same kernel
+    (profiles/r02_c4_wave_ncu.json: l1tex__data_pipe_lsu_wavefronts); rate and clock are this run's."""
+    import torch
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_c4_wave_ncu.json")))
+        wf = prof["l1_data_pipe_lsu_wavefronts_pct_of_peak"] / 100.0 * prof["sm_cycles"] * torch.cuda.get_device_properties(dev).multi_processor_count / prof["ray_steps"]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        try:
+            mhz = float(torch.cuda.clock_rate(dev))
+            if not (500 < mhz < 4000):
+                mhz = 1965.0
+        except Exception:
+            mhz = 1965.0
+        peak = sms * mhz * 1e6
+        ach = res["g_ray_steps_per_s"] * 1e9 * wf
+        return {"bound": "l1-data-pipe", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G wavefronts/s", "frac": ach / peak, "traffic": prof.get("dram_bytes_per_launch"),
+                "wavefronts_per_ray_step": wf, "roof_g_ray_steps_per_s": peak / wf / 1e9, "sm_mhz": mhz, "num_sms": sms,
+                "source": "wavefronts per ray-step and DRAM bytes per launch from profiles/r02_c4_wave_ncu.json (ncu --set full of this kernel on this workload); "
+                          "rate from this run, clock = the SM clock nvidia-smi reports now"}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def other_configs(dev, names=("c2", "c3", "c4")):
     out = {}
     for nm in names:
         t0 = time.time()
         try:
             out[nm] = run_config(nm, dev, with_ref_cuda=nm in ("c2", "c4"))
+            if nm == "c4":
+                out[nm]["roofline"] = _c4_roofline(out[nm], dev)
             out[nm]["wall_s"] = round(time.time() - t0, 1)
         except Exception as e:                                                # a leg that fails must not take the bench line with it
             out[nm] = {"error": "%s: %s" % (type(e).__name__, e)}

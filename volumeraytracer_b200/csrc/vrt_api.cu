@@ -392,6 +392,30 @@ extern "C" {
 const char *vrt_last_error(void) { return g_last_error.c_str(); }
 const char *vrt_version(void) { return "volumeraytracer_b200 0.1 (sm_100a)"; }
 uint64_t vrt_launch_count(void) { return g_launches.load(); }
+#ifdef VRT_CHECK
+// negative control for the test: one deliberately failing check (thread 0 of one warp)
+__global__ void chk_selftest_kernel() { VRT_CHK(threadIdx.x != 0); }
+VRT_API int vrt_check_selftest(int device)
+{
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    chk_selftest_kernel<<<1, 32>>>();
+    VRT_CUDA(cudaDeviceSynchronize());
+    return VRT_OK;
+}
+// bounds-checked build only: out-of-range accesses the kernels have counted on `device` since the library was loaded
+VRT_API int vrt_check_violations(int device, uint64_t *count)
+{
+    if (!count) return fail(VRT_ERR_INVALID, "count is null");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VRT_ERR_CUDA, "cudaSetDevice failed");
+    unsigned long long v = 0;
+    VRT_CUDA(cudaDeviceSynchronize());
+    VRT_CUDA(cudaMemcpyFromSymbol(&v, vrt::g_vrt_violations, sizeof v));
+    *count = v;
+    return VRT_OK;
+}
+#endif
 
 int vrt_device_count(int *count)
 {
@@ -1248,6 +1272,7 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     if (n == 0) return VRT_OK;
     MarchParams p;
     p.volume = s->d_volume; p.translucency = s->d_translucency;
+    p.vol_bytes = storage_bytes(s); p.nvox = s->nvox;
     p.by = (uint32_t)s->bounds[1]; p.bz = (uint32_t)s->bounds[2];
     p.limx = (uint32_t)((s->bounds[0] - 1) & 0xFFFF); p.limy = (uint32_t)((s->bounds[1] - 1) & 0xFFFF); p.limz = (uint32_t)((s->bounds[2] - 1) & 0xFFFF);
     p.limx16 = p.limx << 16; p.limy16 = p.limy << 16; p.limz16 = p.limz << 16;

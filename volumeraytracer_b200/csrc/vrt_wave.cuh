@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
         p.st_it[i] = m.iterations - 1u;                                                          // cu:333
         if (LIVE) p.st_light[i] = 0xFFFFFFFFu;                                                   // cu:332
         const uint32_t key = wave_key(px, py, pz, p);
+        VRT_CHK(key < p.K);
         p.key_of_ray[i] = key;
         atomicAdd(&p.hist[0][key], 1u);
         p.order[1][i] = (uint32_t)i;                                                             // "previous list" of round 0: everybody
@@ -218,7 +219,13 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
         {
             const uint32_t ray = p.order[cur ^ 1][i];
             const uint32_t k = p.key_of_ray[ray];
-            if (k != kWaveDone) p.order[cur][atomicAdd(&p.bin_off[tail ? p.K : k], 1u)] = ray;
+            VRT_CHK(ray < m.n && (k == kWaveDone || k < p.K));
+            if (k != kWaveDone)
+            {
+                const uint32_t slot = atomicAdd(&p.bin_off[tail ? p.K : k], 1u);
+                VRT_CHK(slot < alive);
+                p.order[cur][slot] = ray;
+            }
         }
         grid.sync();
         // ---- march: persistent warps pull rays from the brick-sorted list ------------------------------------------------------
@@ -250,6 +257,7 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                             if (idx < alive)
                             {
                                 ray = p.order[cur][idx];
+                                VRT_CHK(ray < m.n);
                                 px = p.st_pos[(size_t)ray * 3]; py = p.st_pos[(size_t)ray * 3 + 1]; pz = p.st_pos[(size_t)ray * 3 + 2];
                                 dx = p.st_dir[(size_t)ray * 3]; dy = p.st_dir[(size_t)ray * 3 + 1]; dz = p.st_dir[(size_t)ray * 3 + 2];
                                 it = p.st_it[ray];
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         if (moved >= 0x10000u)
                         {
                             const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
+                            VRT_CHK(cell < m.nvox);
                             if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
                             load_corners<VoxT>(q, m, cell);
                         }
@@ -343,6 +352,7 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         p.st_it[ray] = it;
                         if (LIVE) p.st_light[ray] = brightness;
                         const uint32_t key = wave_key(px, py, pz, p);
+                        VRT_CHK(key < p.K);
                         p.key_of_ray[ray] = key;
                         atomicAdd(&p.hist[cur ^ 1][key], 1u);
                         have = false;

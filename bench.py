@@ -214,7 +214,7 @@ def workload_config(n_gpus):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 
-def sass_block_lengths():
+def sass_block_lengths(kver=9):
     """SASS lengths of the marcher's blocks: the committed profiles/*_sass_blocks.json, checked against the shipped binary when the
     CUDA binary tools are on the box (tools/sass_blocks.py is re-run and the opcode-stream hashes compared)."""
     path = os.path.join(ROOT, "profiles", "r02_sass_blocks.json")
@@ -227,7 +227,9 @@ def sass_block_lengths():
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import sass_blocks
-        live = sass_blocks.analyse(sass_blocks.disassemble(os.path.join(ROOT, "volumeraytracer_b200", "libvrt_b200.so"), sass_blocks.DEFAULT_KERNEL))
+        kernel = sass_blocks.DEFAULT_KERNEL.replace("ELi9E", "ELi%dE" % kver)
+        live = sass_blocks.analyse(sass_blocks.disassemble(os.path.join(ROOT, "volumeraytracer_b200", "libvrt_b200.so"), kernel))
+        live["kernel"] = kernel
     except BaseException:
         live = None
     if live is not None:
@@ -244,7 +246,10 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
     of the kernel was issued, COUNTED IN THIS RUN by an instrumented copy of the kernel) x (the block's SASS length); peak = SMs x 4
     schedulers x SM clock sampled in this run."""
     import torch
-    blocks, src = sass_block_lengths()
+    # the kernel the timed passes ran: KVER 11 (no per-cell clear test) on a scene without any possibly opaque voxel, else KVER 9; the
+    # instrumented copy (KVER 10) has the block structure of both and counts the same block executions on such a scene
+    kver = 11 if (scene.get_option(vrt.VRT_INFO_ALL_CLEAR) == 1 and scene.get_option(vrt.VRT_OPT_ALL_CLEAR_KERNEL) == 1) else 9
+    blocks, src = sass_block_lengths(kver)
     if blocks is None:
         return None
     scene.set_option(vrt.VRT_OPT_KERNEL, 10)               # allocates / zeroes the counters
@@ -277,7 +282,7 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
             "warp_instructions_per_warp_step": warp_instr / max(warp_steps, 1),
             "lane_efficiency": cnt[7] / max(32 * warp_steps, 1), "reloads_per_warp_step": cnt[3] / max(warp_steps, 1),
             "block_issue_counts": dict(zip(names + ["lane_steps", "reload_partial"], cnt)), "block_sass_lengths": b, "sass_lengths_source": src,
-            "num_sms": num_sms, "sm_mhz": sm_mhz, "launch_ms": launch_s * 1e3,
+            "num_sms": num_sms, "sm_mhz": sm_mhz, "launch_ms": launch_s * 1e3, "kernel_variant": kver,
             "how": "counts from one extra pass of the instrumented kernel copy (VRT_OPT_KERNEL 10, outside the timed region); "
                    "time and clock from the timed region; cross-check against ncu smsp__inst_executed.sum in profiles/"}
 

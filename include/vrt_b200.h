@@ -90,7 +90,7 @@ enum {
                                    packed f32x2 + fast loop for cells without a possibly opaque corner, 6 = 3 + empty-space fast path
                                    (opt-in: coherent bundles through mostly empty volumes).  Chosen implicitly, not settable: 9 = 3
                                    specialised for invscale == (1,1,1) (same bits, fewer instructions; what 0/3 resolve to in that
-                                   case), 4 = brick layout (VRT_SCENE_LAYOUT_BRICK), 8 = host rounding (VRT_TRACE_ROUND_HOST), 2 for
+                                   case), 11 = 9 without the per-cell clear test (scenes without any possibly opaque voxel, VRT_OPT_ALL_CLEAR_KERNEL), 4 = brick layout (VRT_SCENE_LAYOUT_BRICK), 8 = host rounding (VRT_TRACE_ROUND_HOST), 2 for
                                    path output; 5 / 7 = texture / z-pair layouts (study build only) */
     VRT_OPT_BLOCK_THREADS = 1,  /* 32..256, multiple of 32 (the marcher is compiled with __launch_bounds__(256, 4)) */
     VRT_OPT_REFILL        = 2,  /* 0: one ray per thread, no refill; 1..32: a warp fetches new rays when >= this many lanes are idle */
@@ -110,6 +110,10 @@ enum {
     VRT_OPT_WAVE_TAIL_PERMILLE = 11, /* when at most this share of the batch is still alive, the rest is marched without bricks (default 20) */
     VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = occupancy limit) */
     VRT_OPT_WAVE_REFILL   = 14, /* a warp takes new rays from the brick-sorted list when at least this many lanes are idle (default 8) */
+    VRT_OPT_ALL_CLEAR_KERNEL = 18, /* 1 (default): a scene in which NO voxel can make a sample opaque (channel 3 carries the sign bit everywhere; counted once at
+                                   scene creation, VRT_INFO_ALL_CLEAR) is marched by a variant of the default kernel without the per-cell clear test (KVER 11,
+                                   chosen implicitly like 9: same bits); 0: always the kernel with the test */
+    VRT_INFO_ALL_CLEAR    = 103, /* read-only: 1 if no voxel of the scene has a non-negative channel 3 */
     VRT_INFO_WAVE_ROUNDS  = 102, /* read-only: rounds the last wavefront launch on this scene took (synchronises) */
     VRT_OPT_REGION_ROUNDS = 7,  /* accepted for compatibility, unused (the wavefront marcher runs as many rounds as the batch needs) */
     VRT_INFO_EMPTY_PERMILLE = 100, /* read-only (vrt_scene_get_option): share of voxels that are empty space (zero gradient, non-positive

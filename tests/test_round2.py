@@ -313,6 +313,34 @@ def test_normalise_accepts_rays_in_the_last_half_voxel(vrt, oracle, kind):
     sc.close()
 
 
+@pytest.mark.parametrize("volk,dirk,live", [("f32", "f32", False), ("i16", "i16", False), ("f32", "i16", True), ("i16", "f32", True)])
+def test_all_clear_scene_uses_the_kernel_without_the_cell_test(vrt, oracle, volk, dirk, live):
+    """A scene in which no voxel can make a sample opaque (channel 3 negative everywhere) is marched by KVER 11, the default kernel
+    without the per-cell clear test; one possibly opaque voxel (channel 3 == +0: tr = 0x7FFFFFFF) switches it off.  Same bits as the
+    kernel with the test and as the oracle."""
+    for opaque_voxels in (0, 1):
+        ior, tr = S.random_scene((40, 36, 44), seed=31, kind="f32" if volk == "f32" else "u32", opaque_fraction=0.0)
+        ob, iorlog, planes, trc = oracle.prep((40, 36, 44), ior, tr)
+        trc = trc.copy()
+        if live:
+            trc[trc != 0] -= np.uint32(1 << 24)
+        if opaque_voxels:
+            trc.reshape(-1)[trc.size // 2 + 7] = np.uint32(0x7FFFFFFF)          # (0x7FFFFFFF - tr) / 0x10000 == 0: sign bit clear
+        vol = oracle.fold(planes, trc)
+        t = vrt.TraceRaysCu(ob, planes, trc, keep_i16=(volk == "i16" and live))
+        assert t.get_option(vrt.VRT_INFO_ALL_CLEAR) == (0 if opaque_voxels else 1)
+        pos, d = S.random_rays(ob, 30000, seed=9, dir_kind=dirk, scale=1.1)
+        pos = pos - np.uint32(0x10000) + np.uint32(0x4321)
+        isc = [1.0, 1.0, 1.0]
+        minb = 0x40000000 if live else 0
+        want = oracle.trace(vol, ob, pos, d, isc, 500, translucency=trc if live else None, min_brightness=minb, round_mode=oracle.ROUND_DEVICE)
+        for allclear in (1, 0):
+            t.set_option(vrt.VRT_OPT_ALL_CLEAR_KERNEL, allclear)
+            got = t.trace_rays_cu(pos, d, isc, minb, 500, live_translucency=live)
+            _assert_same(got, want[:4], "all-clear kernel option %d, %d opaque voxel(s), %s/%s" % (allclear, opaque_voxels, volk, dirk))
+        t.close()
+
+
 def test_host_call_chunk_schedule_on_a_large_batch(vrt, oracle):
     """vrt_trace cuts a large batch into whole waves of the persistent grid with a small first and last chunk (head and tail of the
     copy pipeline).  5 M + 17 rays is past the point where that schedule starts: every ray must come back, in place, with the bits

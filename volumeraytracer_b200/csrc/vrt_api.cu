@@ -83,6 +83,7 @@ struct vrt_scene
     bool      bricked = false;     // VRT_SCENE_LAYOUT_BRICK
     bool      paired = false;      // VRT_SCENE_LAYOUT_PAIR: d_volume holds {voxel, z neighbour} per cell (2 x nvox float4)
     double    flat_fraction = 0.0; // share of voxels with zero gradient and non-positive extra channel (set by apply_storage)
+    bool      all_clear = false;   // no voxel of the scene can make a sample opaque: channel 3 carries the sign bit everywhere (set by apply_storage)
     cudaArray_t tex_array = nullptr;   // VRT_SCENE_LAYOUT_TEXTURE: block-linear copy + point-sampled texture object
     cudaTextureObject_t tex = 0;
     uint64_t  nb[3] = {1, 1, 1};   // bricks per axis
@@ -105,7 +106,7 @@ struct vrt_scene
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: kStatSlots block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
-    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8}, opt_allclear{1};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -209,18 +210,24 @@ static int alloc_scene_buffers(vrt_scene *s)
 //   * re-orders it into 2x2x2 bricks when VRT_SCENE_LAYOUT_BRICK is set.
 // linearise() is the inverse, used by vrt_scene_download / vrt_scene_export_device.
 
+__device__ __forceinline__ bool sign_clear(float v) { return (__float_as_uint(v) >> 31) == 0u; }
+__device__ __forceinline__ bool sign_clear(short v) { return v >= 0; }
+// count[0]: voxels that are empty space (zero gradient, non-positive channel 3); count[1]: voxels whose channel 3 does NOT carry the
+// sign bit, i.e. voxels that can make a sample opaque (cu:343).  A scene without any lets the marcher drop its per-cell test (KVER 11).
 template <typename T>
 __global__ void count_flat_kernel(const T *vol, unsigned long long nvox, unsigned long long *count)
 {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool flat = false;
+    bool flat = false, solid = false;
     if (i < nvox)
     {
         const T *v = vol + i * 4;
         flat = v[0] == T(0) && v[1] == T(0) && v[2] == T(0) && v[3] <= T(0);
+        solid = sign_clear(v[3]);
     }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, flat);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, flat), m2 = __ballot_sync(0xFFFFFFFFu, solid);
     if ((threadIdx.x & 31u) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31u) == 0 && m2) atomicAdd(count + 1, (unsigned long long)__popc(m2));
 }
 
 __global__ void widen_i16_kernel(const short *in, float *out, unsigned long long n)
@@ -254,17 +261,18 @@ static int apply_storage(vrt_scene *s, unsigned flags)
     const unsigned long long nelem = s->nvox * (unsigned long long)(s->dim + 1);
     if (s->dim == 3)   // how much of the volume is empty space?  (decides whether the default kernel takes the fast path)
     {
-        unsigned long long *d_cnt = nullptr, h_cnt = 0;
-        VRT_CUDA(cudaMalloc((void **)&d_cnt, 8));
-        VRT_CUDA(cudaMemset(d_cnt, 0, 8));
+        unsigned long long *d_cnt = nullptr, h_cnt[2] = {0, 0};
+        VRT_CUDA(cudaMalloc((void **)&d_cnt, 16));
+        VRT_CUDA(cudaMemset(d_cnt, 0, 16));
         const unsigned grid = (unsigned)((s->nvox + 255) / 256);
         if (s->dtype == VRT_F32) count_flat_kernel<float><<<grid, 256>>>((const float *)s->d_volume, s->nvox, d_cnt);
         else                     count_flat_kernel<short><<<grid, 256>>>((const short *)s->d_volume, s->nvox, d_cnt);
         ++g_launches;
-        cudaError_t e = cudaMemcpy(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost);
         cudaFree(d_cnt);
         VRT_CUDA(e);
-        s->flat_fraction = (double)h_cnt / (double)s->nvox;
+        s->flat_fraction = (double)h_cnt[0] / (double)s->nvox;
+        s->all_clear = h_cnt[1] == 0;
     }
     if (s->owns && s->dtype == VRT_I16 && s->dim == 3 && !(flags & VRT_SCENE_KEEP_I16) && nelem * 4ull <= (24ull << 30))
     {
@@ -692,6 +700,7 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_WAVE_TAIL_PERMILLE: if (v < 0 || v > 1000) return fail(VRT_ERR_INVALID, "wavefront tail must be 0..1000 permille"); s->opt_wave_tail = v; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: if (v < 0 || v > 8) return fail(VRT_ERR_INVALID, "wavefront CTAs per SM must be 0..8"); s->opt_wave_ctas = v; break;
     case VRT_OPT_WAVE_REFILL:    if (v < 1 || v > 32) return fail(VRT_ERR_INVALID, "wavefront refill threshold must be 1..32"); s->opt_wave_refill = v; break;
+    case VRT_OPT_ALL_CLEAR_KERNEL: if (v < 0 || v > 1) return fail(VRT_ERR_INVALID, "must be 0 or 1"); s->opt_allclear = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -716,6 +725,8 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_WAVE_TAIL_PERMILLE: *v = s->opt_wave_tail; break;
     case VRT_OPT_WAVE_CTAS_PER_SM: *v = s->opt_wave_ctas; break;
     case VRT_OPT_WAVE_REFILL: *v = s->opt_wave_refill; break;
+    case VRT_OPT_ALL_CLEAR_KERNEL: *v = s->opt_allclear; break;
+    case VRT_INFO_ALL_CLEAR: *v = s->all_clear ? 1 : 0; break;
     case VRT_INFO_WAVE_ROUNDS: *v = s->last_wave_rounds_host(); break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
     case VRT_INFO_NUM_SMS: *v = s->num_sms; break;
@@ -748,7 +759,7 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     vrt_scene *s = nullptr;
     int rc = new_scene(&s, device, src->dim, src->bounds, src->dtype);
     if (rc) return rc;
-    s->store = src->store; s->bricked = src->bricked; s->flat_fraction = src->flat_fraction;
+    s->store = src->store; s->bricked = src->bricked; s->flat_fraction = src->flat_fraction; s->all_clear = src->all_clear;
     for (int d = 0; d < 3; ++d) { s->nb[d] = src->nb[d]; s->ior_bounds[d] = src->ior_bounds[d]; }
     s->ior_dtype = src->ior_dtype;
     s->opt_kernel = src->opt_kernel.load(); s->opt_block = src->opt_block.load(); s->opt_refill = src->opt_refill.load();
@@ -756,7 +767,7 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
     s->opt_wave = src->opt_wave.load(); s->opt_wave_margin = src->opt_wave_margin.load(); s->opt_wave_check = src->opt_wave_check.load();
     s->opt_wave_tail = src->opt_wave_tail.load(); s->opt_wave_ctas = src->opt_wave_ctas.load();
-    s->opt_wave_refill = src->opt_wave_refill.load();
+    s->opt_wave_refill = src->opt_wave_refill.load(); s->opt_allclear = src->opt_allclear.load();
     *out = s;
     return VRT_OK;
 }
@@ -865,6 +876,7 @@ struct SceneHeader
     uint64_t bounds[3], nb[3], ior_bounds[3];
     double   flat_fraction;
     int64_t  opt[8];
+    int32_t  all_clear, pad_;
 };
 static_assert(sizeof(SceneHeader) <= 256, "header must fit the staging buffer");
 
@@ -1014,7 +1026,7 @@ int vrt_scene_broadcast(vrt_comm *c, int root, vrt_scene *src, vrt_scene **out, 
         h.magic = 0x56525442u; h.dim = src->dim; h.dtype = src->dtype; h.store = src->store; h.bricked = src->bricked;
         h.has_tr = src->d_translucency != nullptr; h.has_ior = src->d_ior != nullptr; h.ior_dtype = src->ior_dtype;
         for (int d = 0; d < 3; ++d) { h.bounds[d] = src->bounds[d]; h.nb[d] = src->nb[d]; h.ior_bounds[d] = src->ior_bounds[d]; }
-        h.flat_fraction = src->flat_fraction;
+        h.flat_fraction = src->flat_fraction; h.all_clear = src->all_clear ? 1 : 0; h.pad_ = 0;
         h.opt[0] = src->opt_kernel; h.opt[1] = src->opt_block; h.opt[2] = src->opt_refill; h.opt[3] = src->opt_chunk;
         h.opt[4] = src->opt_poll; h.opt[5] = src->opt_max_ctas; h.opt[6] = src->opt_region; h.opt[7] = src->opt_rounds;
         VRT_CUDA(cudaMemcpyAsync(c->d_hdr, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
@@ -1028,7 +1040,7 @@ int vrt_scene_broadcast(vrt_comm *c, int root, vrt_scene *src, vrt_scene **out, 
     if (!is_root)
     {
         vrt_scene proto;                       // geometry carrier for clone_empty / alloc_replica
-        proto.dim = h.dim; proto.dtype = h.dtype; proto.store = h.store; proto.bricked = h.bricked != 0; proto.flat_fraction = h.flat_fraction;
+        proto.dim = h.dim; proto.dtype = h.dtype; proto.store = h.store; proto.bricked = h.bricked != 0; proto.flat_fraction = h.flat_fraction; proto.all_clear = h.all_clear != 0;
         proto.ior_dtype = h.ior_dtype; proto.nvox = 1;
         for (int d = 0; d < 3; ++d) { proto.bounds[d] = h.bounds[d]; proto.nb[d] = h.nb[d]; proto.ior_bounds[d] = h.ior_bounds[d]; }
         for (int d = 0; d < h.dim; ++d) proto.nvox *= h.bounds[d];
@@ -1093,6 +1105,16 @@ static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, 
         if (per_sm < 1) per_sm = 1;
         const int cap = (int)s->opt_max_ctas.load();
         if (cap > 0 && cap < per_sm) per_sm = cap;
+        if (MarchBounds<VoxT, LIVE, PATH, KVER>::kNine && cap == 0 && per_sm == 9)
+        {
+            // a batch of equally long rays (config 5: every ray runs the cap) takes ceil(n / resident rays) waves: with few waves one CTA
+            // fewer per SM can mean one partial wave fewer (a 2 M-ray shard: 14 waves of 8 CTAs against 13 of 9, each 9/8/1.03 as long)
+            auto cost = [&](int c) {
+                const unsigned long long per_wave = (unsigned long long)s->num_sms * c * block;
+                return (double)((p.n + per_wave - 1) / per_wave) * c / (c == 9 ? 1.03 : 1.0);
+            };
+            if (cost(8) < cost(9)) per_sm = 8;
+        }
         const unsigned long long want = (p.n + block - 1) / block;
         grid = (unsigned)std::min<unsigned long long>((unsigned long long)per_sm * s->num_sms, want);
     }
@@ -1121,6 +1143,7 @@ static cudaError_t launch3_k(const vrt_scene *s, const MarchParams &p, bool path
     case 7: return launch3<VoxT, DIR_I16, LIVE, false, 7>(s, p, block, st);
 #endif
     case 9: return launch3<VoxT, DIR_I16, LIVE, false, 9>(s, p, block, st);
+    case 11: return launch3<VoxT, DIR_I16, LIVE, false, 11>(s, p, block, st);
     case 10: return launch3<float, false, false, false, 10>(s, p, block, st);      // enqueue_march only selects it for this instantiation
     default: return launch3<VoxT, DIR_I16, LIVE, false, 3>(s, p, block, st);
     }
@@ -1317,6 +1340,8 @@ static int enqueue_march(const vrt_scene *s, uint64_t n, const uint32_t *d_pos, 
     }
     p.stats = kver == 10 ? s->d_stats : nullptr;
     if (kver == 3 && !path && p.invx == 1.0f && p.invy == 1.0f && p.invz == 1.0f) kver = 9;   // unit invscale: two multiplies fewer per step, same bits
+    if (kver == 9 && s->all_clear && s->opt_allclear.load() != 0) kver = 11;                  // ... and no voxel that could make a sample opaque: no per-cell test
+    if (kver == 11 && s->store == VRT_F32 && !(flags & VRT_TRACE_LIVE_TRANSLUCENCY) && s->opt_block.load() > 128) kver = 9;   // that instantiation is compiled for 128-thread CTAs (MarchBounds)
     const bool hostr = flags & VRT_TRACE_ROUND_HOST;
     if (hostr)
     {
@@ -1532,6 +1557,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
 
     // rays per pipelined chunk: copies of chunk i+1 / i-1 overlap the march of chunk i on the other stream
     uint64_t chunk = (uint64_t)s->opt_chunk.load();
+    uint64_t chunk_wave = (uint64_t)s->num_sms * 1024;                      // rays resident at once (set below when the chunk size is chosen here)
     // at least 2^17 rays per chunk (one wave of the persistent grid), at most 16 chunks: config 2 (1 M rays) through pageable buffers
     // runs 8 chunks at 224 G ray-steps/s instead of 2 chunks at 190
     if (chunk == 0 && n > (1u << 17))
@@ -1540,9 +1566,14 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         // rays all run equally long (config 5) a chunk of 131 072 rays leaves 13 % of the grid idle for a whole ray-time, which is
         // what a 2 M-ray shard of the strong-scaling run paid in every one of its 16 chunks (e2e 2174 -> see DESIGN.md section 7)
         uint64_t per_sm = 1024;                                             // 64 registers per thread
+        if (s->all_clear && s->opt_allclear.load() != 0 && s->store == VRT_F32 && dim == 3 && !(flags & (VRT_TRACE_LIVE_TRANSLUCENCY | VRT_TRACE_PATHS | VRT_TRACE_ROUND_HOST)) &&
+            invscale[0] == 1.0f && invscale[1] == 1.0f && invscale[2] == 1.0f && s->opt_block.load() <= 128 && (s->opt_kernel.load() == 0 || s->opt_kernel.load() == 3) &&
+            !s->bricked && !s->tex && !s->paired)
+            per_sm = 1152;                                                  // the all-clear kernel: 9 CTAs of 128 threads (MarchBounds)
         const int64_t cap = s->opt_max_ctas.load(), blk = s->opt_block.load();
         if (cap > 0) per_sm = std::min<uint64_t>(per_sm, (uint64_t)(cap * blk));
         const uint64_t wave = std::max<uint64_t>(1, (uint64_t)s->num_sms * per_sm);
+        chunk_wave = wave;
         const uint64_t m = std::max<uint64_t>(1, ((n + 15) / 16 + wave / 2) / wave);
         chunk = std::max<uint64_t>(1u << 17, m * wave);
     }
@@ -1596,7 +1627,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     uint64_t edge = 0;
     if (s->opt_chunk.load() == 0 && !want_path && region == 0 && s->dim == 3)
     {
-        const uint64_t wave = std::max<uint64_t>(1u << 17, (uint64_t)s->num_sms * 1024);
+        const uint64_t wave = std::max<uint64_t>(1u << 17, chunk_wave);
         if (chunk >= 2 * wave && n >= 4 * chunk) edge = wave;
     }
     uint64_t index = 0;

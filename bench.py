@@ -414,6 +414,16 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t1
     barrier()
     e2e_value = steps_global * e2e_steps / reduce_max(e2e_s) / 1e9
+    # the same with the D2H copies issued by the calling thread (no read-back helper thread): what the helper buys on this host
+    os.environ["VRT_NO_READBACK_THREAD"] = "1"
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scene.trace_host_buffers(h_pos, h_dir, isc, 0, iters, h_epos, h_edir, h_eit, h_light)
+    e2e_nohelper_s = time.perf_counter() - t1
+    barrier()
+    del os.environ["VRT_NO_READBACK_THREAD"]
+    e2e_nohelper = steps_global * e2e_steps / reduce_max(e2e_nohelper_s) / 1e9
     e2e_ok = bool(np.array_equal(h_eit, eit.cpu().numpy().view(np.uint32)) and np.array_equal(h_epos, epos.cpu().numpy().view(np.uint32)))
     e2e_ok_all = reduce_sum(0 if e2e_ok else 1) == 0
     whole_batch_steps = int(batch.arrays["eit"].astype(np.int64).sum()) if rank == 0 else 0      # rank 0 reads ALL ranks' results out of the one batch
@@ -508,6 +518,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "G ray-steps/s", "h2d_bytes_per_step": n_total * 24, "d2h_bytes_per_step": n_total * 32,
                     "steps": e2e_steps, "matches_device_run": e2e_ok_all, "whole_batch_ray_steps_read_by_rank0": whole_batch_steps,
                     "call": "vrt_trace (C ABI) on each rank's contiguous chunk of ONE batch held in PAGEABLE host memory shared by the ranks; results in place",
+                    "single_thread_readback_value": e2e_nohelper,
                     "pinned_value": e2e_pinned, "pinned_note": "same call with the chunk cudaHostRegister'ed (registration outside the timed region)"},
             "gpu_launches": launches_global, "roofline": roof if roof is not None else roof_hbm, "roofline_hbm": roof_hbm, "roofline_l2": roof_l2,
             "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast": bcast,

@@ -23,7 +23,12 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <cstdlib>
 #include <deque>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1391,9 +1396,61 @@ static bool batch_is_incoherent(uint64_t n, int dim, const uint32_t *pos, const 
 // Per host thread and device: the two pipeline streams of vrt_trace and a pinned/device staging pair for small
 // batches.  Created on first use, reused by every later call of that thread (stream creation and pinned allocation
 // cost more than a small trace), released when the thread exits.
+// Read-back helper of vrt_trace: a thread that issues the D2H copies of finished chunks while the calling thread is still staging
+// later chunks.  With PAGEABLE host buffers both directions block the thread that issues them for the whole copy (the runtime stages
+// through its own pinned buffers), so one thread pays H2D + D2H -- for config 5 that is 0.94 GB per pass, about as long as the march
+// itself, and at 8 ranks per host it WAS the critical path of the end-to-end call.  Two threads pay max(H2D, D2H).
+class Drainer
+{
+public:
+    Drainer() : _stop(false), _busy(0) { _th = std::thread([this] { loop(); }); }
+    ~Drainer()
+    {
+        { std::lock_guard<std::mutex> lk(_mu); _stop = true; }
+        _cv.notify_all();
+        if (_th.joinable()) _th.join();
+    }
+    void push(std::function<void()> job)
+    {
+        { std::lock_guard<std::mutex> lk(_mu); _q.push_back(std::move(job)); ++_busy; }
+        _cv.notify_one();
+    }
+    // blocks until at most `limit` jobs are queued or running
+    void wait_below(size_t limit)
+    {
+        std::unique_lock<std::mutex> lk(_mu);
+        _done.wait(lk, [&] { return _busy <= limit; });
+    }
+private:
+    void loop()
+    {
+        for (;;)
+        {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(_mu);
+                _cv.wait(lk, [&] { return _stop || !_q.empty(); });
+                if (_q.empty()) return;
+                job = std::move(_q.front());
+                _q.pop_front();
+            }
+            job();
+            { std::lock_guard<std::mutex> lk(_mu); --_busy; }
+            _done.notify_all();
+        }
+    }
+    std::thread _th;
+    std::mutex _mu;
+    std::condition_variable _cv, _done;
+    std::deque<std::function<void()>> _q;
+    bool _stop;
+    size_t _busy;
+};
+
 struct ThreadCtx
 {
     static constexpr size_t kSmallBytes = 1u << 20;
+    std::unique_ptr<Drainer> drainer;      // created on the first large pipelined call of this thread
     int device = -1;
     static constexpr size_t kEvents = 128;
     cudaStream_t st[2] = {nullptr, nullptr}, in = nullptr, out = nullptr;
@@ -1601,23 +1658,37 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     auto note = [&](cudaError_t e) {
         if (e != cudaSuccess && result == VRT_OK) { result = fail(e == cudaErrorMemoryAllocation ? VRT_ERR_NOMEM : VRT_ERR_CUDA, cudaGetErrorString(e)); cudaGetLastError(); }
     };
+    // the D2H copies of one chunk; runs on the calling thread or on the read-back helper (errors go to `drain_error`, merged below)
+    std::atomic<int> drain_error{(int)cudaSuccess};
+    const cudaStream_t out_stream = t_ctx.out;
+    const int dev_id = s->device;
+    auto drain_chunk = [=, &drain_error](const Pending &c, bool on_helper) {
+        if (on_helper) cudaSetDevice(dev_id);
+        cudaStream_t q = out_stream;
+        const size_t b_pos = (size_t)c.m * dim * 4, b_dir = (size_t)c.m * dim * ds, b_u32 = (size_t)c.m * 4;
+        auto chk = [&](cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; drain_error.compare_exchange_strong(ok, (int)e); cudaGetLastError(); } };
+        chk(cudaStreamWaitEvent(q, c.marched, 0));
+        if (drain_error.load() == (int)cudaSuccess)
+        {
+            chk(cudaMemcpyAsync(epos + c.off * dim, c.buf, b_pos, cudaMemcpyDeviceToHost, q));
+            chk(cudaMemcpyAsync((char *)edir + c.off * dim * ds, c.buf + c.o_dir, b_dir, cudaMemcpyDeviceToHost, q));
+            chk(cudaMemcpyAsync(eit + c.off, c.buf + c.o_eit, b_u32, cudaMemcpyDeviceToHost, q));
+            chk(cudaMemcpyAsync(light + c.off, c.buf + c.o_light, b_u32, cudaMemcpyDeviceToHost, q));
+            if (want_path) chk(cudaMemcpyAsync(path + c.off * iterations * dim, c.buf + c.o_path, c.b_path, cudaMemcpyDeviceToHost, q));
+            if (c.flag_slot) chk(cudaMemcpyAsync(c.flag_slot, c.buf + c.o_flag, 4, cudaMemcpyDeviceToHost, q));   // pinned: asynchronous
+        }
+        cudaFreeAsync(c.buf, q);
+    };
+    // large batches hand the read-back to the helper thread as soon as a chunk's march is enqueued; small ones keep the old order
+    // (issue everything, then read back oldest first) on the calling thread
+    const bool use_helper = n >= 4 * chunk && !want_path && std::getenv("VRT_NO_READBACK_THREAD") == nullptr;
+    if (use_helper && !t_ctx.drainer) t_ctx.drainer.reset(new Drainer());
+    Drainer *const helper = use_helper ? t_ctx.drainer.get() : nullptr;
     auto drain_front = [&]() {
         Pending c = pending.front();
         pending.pop_front();
         pending_bytes -= c.bytes;
-        cudaStream_t q = t_ctx.out;
-        const size_t b_pos = (size_t)c.m * dim * 4, b_dir = (size_t)c.m * dim * ds, b_u32 = (size_t)c.m * 4;
-        note(cudaStreamWaitEvent(q, c.marched, 0));
-        if (result == VRT_OK)
-        {
-            note(cudaMemcpyAsync(epos + c.off * dim, c.buf, b_pos, cudaMemcpyDeviceToHost, q));
-            note(cudaMemcpyAsync((char *)edir + c.off * dim * ds, c.buf + c.o_dir, b_dir, cudaMemcpyDeviceToHost, q));
-            note(cudaMemcpyAsync(eit + c.off, c.buf + c.o_eit, b_u32, cudaMemcpyDeviceToHost, q));
-            note(cudaMemcpyAsync(light + c.off, c.buf + c.o_light, b_u32, cudaMemcpyDeviceToHost, q));
-            if (want_path) note(cudaMemcpyAsync(path + c.off * iterations * dim, c.buf + c.o_path, c.b_path, cudaMemcpyDeviceToHost, q));
-            if (c.flag_slot) note(cudaMemcpyAsync(c.flag_slot, c.buf + c.o_flag, 4, cudaMemcpyDeviceToHost, q));   // pinned: asynchronous
-        }
-        cudaFreeAsync(c.buf, q);
+        drain_chunk(c, false);
     };
     uint32_t *const flag_slots = (uint32_t *)t_ctx.h_stage;
     constexpr uint64_t kFlagSlots = ThreadCtx::kSmallBytes / 4;
@@ -1648,6 +1719,7 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
         if (c.flag_slot) *c.flag_slot = 0;
         c.b_path = want_path ? (size_t)m * iterations * dim * 4 : 0;
         c.bytes = c.o_path + c.b_path;
+        if (helper) helper->wait_below(std::min<size_t>(kWindowChunks - 1, std::max<size_t>(1, kWindowBytes / std::max<size_t>(c.bytes, 1)) - 1));
         while (!pending.empty() && (pending_bytes + c.bytes > kWindowBytes || pending.size() >= kWindowChunks)) drain_front();
         if (result != VRT_OK) break;
         c.buf = nullptr;
@@ -1669,10 +1741,12 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
             if (rc2 && result == VRT_OK) result = rc2;
         }
         note(cudaEventRecord(c.marched, q));
-        pending.push_back(c);
-        pending_bytes += c.bytes;
+        if (helper) helper->push([drain_chunk, c] { drain_chunk(c, true); });
+        else { pending.push_back(c); pending_bytes += c.bytes; }
     }
     while (!pending.empty()) drain_front();
+    if (helper) helper->wait_below(0);
+    if (drain_error.load() != (int)cudaSuccess) note((cudaError_t)drain_error.load());
     cudaStream_t all[4] = {t_ctx.in, t_ctx.st[0], t_ctx.st[1], t_ctx.out};
     for (cudaStream_t q : all) note(cudaStreamSynchronize(q));
     if (result == VRT_OK && index <= kFlagSlots)

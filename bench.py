@@ -287,7 +287,42 @@ def issue_roofline(scene, one_pass, steps_local, launch_s, clocks, peaks, vrt):
                    "time and clock from the timed region; cross-check against ncu smsp__inst_executed.sum in profiles/"}
 
 
+ORIGINAL_AFFINITY = None
+
+
+def restore_affinity():
+    """the CPU legs (cpu_baseline, the reference's CPU / CUDA comparators) get every core the process was given"""
+    if ORIGINAL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, ORIGINAL_AFFINITY)
+        except OSError:
+            pass
+
+
+def bind_near_gpu(gpu_index):
+    """Process placement: run this rank's host threads on the CPUs that NVML names as local to its GPU (the pageable staging copies of the
+    end-to-end leg are host memcpys; across sockets they are slower and vary from run to run).  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        global ORIGINAL_AFFINITY
+        ORIGINAL_AFFINITY = set(allowed)
+        want = sorted(local & allowed)
+        if len(want) >= 2 and len(want) < len(allowed):
+            os.sched_setaffinity(0, want)
+            return {"bound_to_cpus": "%d-%d (%d, NVML affinity of GPU %d)" % (want[0], want[-1], len(want), gpu_index)}
+        return {"bound_to_cpus": None, "why": "NVML affinity covers all allowed CPUs" if want else "no NVML-local CPU is allowed"}
+    except Exception as e:
+        return {"bound_to_cpus": None, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_ours(args, rank, local_rank, world):
+    placement = bind_near_gpu(local_rank)
     import torch
     import volumeraytracer_b200 as vrt
     from volumeraytracer_b200 import workloads as W
@@ -521,11 +556,12 @@ def run_ours(args, rank, local_rank, world):
                     "single_thread_readback_value": e2e_nohelper,
                     "pinned_value": e2e_pinned, "pinned_note": "same call with the chunk cudaHostRegister'ed (registration outside the timed region)"},
             "gpu_launches": launches_global, "roofline": roof if roof is not None else roof_hbm, "roofline_hbm": roof_hbm, "roofline_l2": roof_l2,
-            "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast": bcast,
+            "ray_steps_per_pass": steps_global, "setup_s": round(setup_s, 2), "nccl_broadcast": bcast, "host_placement_rank0": placement,
             "nccl_broadcast_gbs": bcast["gb_per_s"] if bcast else None, "weak_scaling": weak, "config4_scaling": c4,
             "kernel": {"variant": scene.get_option(vrt.VRT_OPT_KERNEL), "block": scene.get_option(vrt.VRT_OPT_BLOCK_THREADS),
                        "refill": scene.get_option(vrt.VRT_OPT_REFILL), "steps_per_poll": scene.get_option(vrt.VRT_OPT_STEPS_PER_POLL)},
         }
+        restore_affinity()
         if world == 1 and not args.no_cpu_baseline:
             line.update(cpu_baseline_and_parity(scene, ior, pos_t, dir_t, epos, edir, eit, side, iters, size))
     del ior
@@ -696,7 +732,7 @@ def main():
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--ray-side", type=int, default=RAY_SIDE)
     ap.add_argument("--iterations", type=int, default=ITERATIONS)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-window", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weak-steps", type=int, default=3, help="N>1: timed passes of the weak-scaling extra (0 = skip)")

@@ -1099,7 +1099,13 @@ static cudaError_t launch3(const vrt_scene *s, const MarchParams &p, int block, 
     auto kern = march3_kernel<VoxT, DIR_I16, LIVE, PATH, KVER>;
     static std::atomic<unsigned long long> carved{0};  // per device: the marcher uses no shared memory, give the unified array to L1
     const unsigned long long bit = 1ull << (s->device & 63);
-    if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    if (!(carved.fetch_or(bit) & bit))
+    {
+        // every CTA reserves 1 KB of shared memory: the smallest carve-out (MaxL1) admits 8 CTAs per SM, the 9-CTA instantiation needs the next one
+        int carve = MarchBounds<VoxT, LIVE, PATH, KVER>::kNine ? 8 : (int)cudaSharedmemCarveoutMaxL1;
+        if (const char *e = std::getenv("VRT_CARVEOUT_PCT")) carve = std::atoi(e);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     unsigned grid;
     if (p.refill == 0) grid = (unsigned)((p.n + block - 1) / block);
     else

@@ -1699,19 +1699,37 @@ int vrt_trace(vrt_scene *s, uint64_t n, const uint32_t *pos, const void *dir, in
     uint32_t *const flag_slots = (uint32_t *)t_ctx.h_stage;
     constexpr uint64_t kFlagSlots = ThreadCtx::kSmallBytes / 4;
 
-    // The first chunk's H2D copy and the last chunk's D2H copy cannot overlap any marching: keep those two chunks small (one wave of
-    // the persistent grid) when the regular chunk is several waves (config 5 on one GPU: 16 chunks of 7 waves; head + tail 4.4 -> ~1 ms)
-    uint64_t edge = 0;
-    if (s->opt_chunk.load() == 0 && !want_path && region == 0 && s->dim == 3)
+    // Chunk schedule.  The first chunk's H2D copy and the last chunk's D2H copy cannot overlap any marching, and a chunk can only be
+    // staged while its predecessors march: when the regular chunk is several waves of the persistent grid, the batch starts with 1, 2,
+    // 4, ... waves (staging pageable memory is ~2.5x as fast as marching the same rays: each chunk is staged before its predecessor
+    // has finished) and ends with ..., 4, 2, 1 waves (the read-back, ~1.9x as fast as the march, follows right behind it), so that head
+    // and tail of the copy pipeline are one wave each instead of one regular chunk (config 5 on one GPU: 6 waves).
+    std::vector<uint64_t> sizes;
     {
         const uint64_t wave = std::max<uint64_t>(1u << 17, chunk_wave);
-        if (chunk >= 2 * wave && n >= 4 * chunk) edge = wave;
+        std::vector<uint64_t> ramp;
+        if (s->opt_chunk.load() == 0 && !want_path && region == 0 && s->dim == 3 && chunk >= 2 * wave)
+            for (uint64_t w = wave; w < chunk; w *= 2) ramp.push_back(w);
+        uint64_t ramp_sum = 0;
+        for (uint64_t w : ramp) ramp_sum += w;
+        if (ramp.empty() || n < 2 * ramp_sum + 2 * chunk) ramp.clear(), ramp_sum = 0;
+        for (uint64_t w : ramp) sizes.push_back(w);
+        uint64_t middle = n - 2 * ramp_sum;
+        // without a ramp (chunks of one wave: a shard of a multi-GPU run) the partial chunk goes FIRST: its launch leaves most of the
+        // machine to the next chunk, which starts at once on the other stream, whereas a partial last chunk runs alone for a whole ray-time
+        if (ramp.empty() && chunk < n && n % chunk != 0) { sizes.push_back(n % chunk); middle -= n % chunk; }
+        while (middle > 0)
+        {
+            const uint64_t m = (middle >= chunk + chunk / 2 || ramp.empty()) ? std::min(chunk, middle) : middle;   // the remainder joins the last regular chunk
+            sizes.push_back(m);
+            middle -= m;
+        }
+        for (size_t i = ramp.size(); i-- > 0;) sizes.push_back(ramp[i]);
     }
     uint64_t index = 0;
-    for (uint64_t off = 0, m = 0; off < n && result == VRT_OK; off += m, ++index)
+    for (uint64_t off = 0, m = 0; index < sizes.size() && result == VRT_OK; off += m, ++index)
     {
-        m = std::min(chunk, n - off);
-        if (edge) m = off == 0 ? edge : (n - off <= chunk + edge ? (n - off > edge ? n - off - edge : n - off) : chunk);
+        m = sizes[index];
         cudaStream_t q = t_ctx.st[index & 1];
         // one stream-ordered allocation per chunk: [pos | dir | eit | light | counter | path]
         Pending c;

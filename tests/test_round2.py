@@ -423,6 +423,35 @@ def test_wavefront_odd_extents_and_extreme_directions(vrt, oracle, shape, volk):
     t.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("volk,dirk,keep", [("f32", "f32", False), ("f32", "i16", False), ("i16", "f32", True), ("i16", "i16", True), ("i16", "f32", False)])
+def test_wavefront_all_clear_variant_is_bit_identical(vrt, oracle, volk, dirk, keep):
+    """A scene without any possibly opaque voxel (VRT_INFO_ALL_CLEAR) is marched by the wavefront kernel's variant that keeps no
+    channel 3 in its cell cache (4 resident CTAs per SM): same bits as the oracle, as the generic wavefront kernel
+    (VRT_OPT_ALL_CLEAR_KERNEL 0) and as the single launch -- incl. rays outside the volume, degenerate directions, the cap flag."""
+    ob, planes, trc, vol, t = _mk(vrt, oracle, (41, 36, 52), 23, volk, opaque=0.0, keep_i16=keep)
+    assert t.get_option(vrt.VRT_INFO_ALL_CLEAR) == 1
+    pos, d = S.random_rays(ob, 60000, seed=29, dir_kind=dirk, scale=1.15)
+    pos = pos - np.uint32(0x10000) + np.uint32(0x0F0F)
+    pos[:40] = np.uint32(0xFFF00000)                              # rays that start outside the volume
+    if dirk == "f32":
+        d[100:200] = 0.0
+        d[200:300] *= np.float32(1e-30)
+        d[300:400] *= np.float32(1e25)
+    for isc, iters in (([1.0, 1.0, 1.0], 600), ([0.9, 1.3, 1.0], 600), ([1.0, 1.0, 1.0], 7)):
+        want = oracle.trace(vol, ob, pos, d, isc, iters, round_mode=oracle.ROUND_DEVICE)
+        for k, margin, check, allclear in ((3, 2, 16, 1), (4, 0, 5, 1), (5, 8, 16, 1), (3, 2, 16, 0), (-1, 2, 16, 1)):
+            t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, margin)
+            t.set_option(vrt.VRT_OPT_WAVE_CHECK, check); t.set_option(vrt.VRT_OPT_ALL_CLEAR_KERNEL, allclear)
+            got = t.trace_rays_cu(pos, d, isc, 0, iters)
+            _assert_same(got, want[:4], "all-clear wavefront k=%d margin=%d check=%d allclear=%d isc=%s %s/%s" % (k, margin, check, allclear, isc, volk, dirk))
+            if k > 0:
+                assert t.get_option(vrt.VRT_INFO_WAVE_ROUNDS) >= 1
+        if iters == 7:
+            assert t.cap_hit() == 1
+    t.close()
+
+
 def test_device_probe_picks_the_marcher_without_a_sync(vrt, oracle):
     """vrt_trace_device on a large volume: a probe KERNEL looks at the device-resident rays and gates the single-launch and the
     wavefront marcher; a shuffled batch runs the wavefront kernel (rounds > 0), a coherent bundle does not (rounds == 0); the

@@ -1192,10 +1192,10 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
 }
 
 // ---- wavefront mode (vrt_wave.cuh): ONE cooperative launch does bucket passes + marching, round by round -------------------
-template <typename VoxT, bool DIR_I16, bool LIVE>
+template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR = false>
 static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
 {
-    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE>;
+    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE, ALLCLEAR>;
     static std::atomic<unsigned long long> carved{0};  // per device: next to no shared memory in use, give the unified array to L1
     const unsigned long long bit = 1ull << (s->device & 63);
     if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -1254,7 +1254,14 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
     cudaError_t err = cudaMemsetAsync(wp.ctl, 0, 256, st);
     if (err == cudaSuccess)
     {
-        if (s->store == VRT_F32)
+        // a scene without any possibly opaque voxel (VRT_INFO_ALL_CLEAR; shipped translucency behaviour): the variant that keeps no channel 3
+        // in its cell cache -- 64 registers, 4 resident CTAs per SM instead of 3 (same bits: vrt_wave.cuh)
+        const bool allclear = s->all_clear && s->opt_allclear.load() != 0 && !live;
+        if (allclear && s->store == VRT_F32)
+            err = di16 ? launch_wave<float, true, false, true>(s, wp, st) : launch_wave<float, false, false, true>(s, wp, st);
+        else if (allclear)
+            err = di16 ? launch_wave<int16_t, true, false, true>(s, wp, st) : launch_wave<int16_t, false, false, true>(s, wp, st);
+        else if (s->store == VRT_F32)
             err = di16 ? (live ? launch_wave<float, true, true>(s, wp, st) : launch_wave<float, true, false>(s, wp, st))
                        : (live ? launch_wave<float, false, true>(s, wp, st) : launch_wave<float, false, false>(s, wp, st));
         else

@@ -39,6 +39,9 @@ namespace cg = cooperative_groups;
 #ifndef VRT_WAVE_MINCTAS
 #define VRT_WAVE_MINCTAS 3     // 3 x 256 threads per SM -> up to 85 registers: no spills (4 CTAs / 64 registers spills the corner cache)
 #endif
+#ifndef VRT_WAVE_MINCTAS_ALLCLEAR
+#define VRT_WAVE_MINCTAS_ALLCLEAR 4   // the all-clear variant keeps 24 instead of 32 cache registers
+#endif
 
 constexpr uint32_t kWaveDone = 0xFFFFFFFFu;
 constexpr int      kWaveThreads = 256;           // threads per CTA
@@ -131,8 +134,13 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t &total, uint
     return before + inc - v;
 }
 
-template <typename VoxT, bool DIR_I16, bool LIVE>
-__global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_kernel(const WaveParams p)
+// ALLCLEAR: the scene has no voxel that could make a sample opaque (counted at scene creation, VRT_INFO_ALL_CLEAR), so the stop test
+// cu:343 cannot fire and channel 3 is neither kept nor interpolated -- the cell cache is march3_kernel's CornersZ (24 instead of 32
+// registers, 24 instead of 30 instructions per sample; same bits, see trilerp_z) and the kernel fits 4 resident CTAs per SM.
+template <bool ALLCLEAR> struct WaveBounds { static constexpr int kMinCtas = ALLCLEAR ? VRT_WAVE_MINCTAS_ALLCLEAR : VRT_WAVE_MINCTAS; };
+
+template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR>
+__global__ void __launch_bounds__(kWaveThreads, (WaveBounds<ALLCLEAR>::kMinCtas)) march3_wave_kernel(const WaveParams p)
 {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const MarchParams &m = p.m;
@@ -142,7 +150,6 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
     const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + tid, gsize = (unsigned long long)gridDim.x * blockDim.x;
 
     __shared__ uint32_t s_scan[kWaveThreads / 32];
-    __shared__ uint32_t s_base;
 
     // ---- phase 0: every ray into the state arrays, first histogram ---------------------------------------------------------
     for (unsigned long long i = gtid; i < (unsigned long long)p.K; i += gsize) { p.hist[0][i] = 0; p.hist[1][i] = 0; }
@@ -239,7 +246,8 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
             uint32_t px = 0, py = 0, pz = 0, it = 0, brightness = 0xFFFFFFFFu, cached_tr = 0, moved = 0xFFFFFFFFu, ray = 0;
             float dx = 0, dy = 0, dz = 0;
             bool have = false, exhausted = false;                                    // exhausted: warp-uniform, the list has been handed out
-            CornersP q;
+            CornersP q;             // cell cache (generic)
+            CornersZ cz;            // cell cache without channel 3 (ALLCLEAR)
             for (;;)
             {
                 if (!exhausted)
@@ -303,7 +311,8 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                             const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
                             VRT_CHK(cell < m.nvox);
                             if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
-                            load_corners<VoxT>(q, m, cell);
+                            if (ALLCLEAR) load_corners_z<VoxT>(cz, m, cell);
+                            else          load_corners<VoxT>(q, m, cell);
                         }
                         if (LIVE)                                                                            // cu:337-341
                         {
@@ -313,9 +322,13 @@ __global__ void __launch_bounds__(kWaveThreads, VRT_WAVE_MINCTAS) march3_wave_ke
                         }
                         unsigned long long gxy, gzw;
                         float gz, gw, sx, sy;
-                        trilerp_packed(q, px, py, pz, gxy, gzw, scale48_const());                            // cu:342
-                        unpack2(gzw, gz, gw);
-                        if (gw > 0.0f) { done = true; it_final = it + 1u; break; }                           // cu:343
+                        if (ALLCLEAR) trilerp_z(cz, px, py, pz, gxy, gz, scale48_const());                   // cu:342; cu:343 cannot fire
+                        else
+                        {
+                            trilerp_packed(q, px, py, pz, gxy, gzw, scale48_const());                        // cu:342
+                            unpack2(gzw, gz, gw);
+                            if (gw > 0.0f) { done = true; it_final = it + 1u; break; }                       // cu:343
+                        }
                         const unsigned long long dxy = fma2(pack2(invx, invy), gxy, pack2(dx, dy));          // cu:344-345
                         dz = __fmaf_rn(invz, gz, dz);
                         unpack2(dxy, dx, dy);

@@ -155,7 +155,7 @@ def _c4_roofline(res, dev):
         ach = res["g_ray_steps_per_s"] * 1e9 * wf
         return {"bound": "l1-data-pipe", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G wavefronts/s", "frac": ach / peak, "traffic": prof.get("dram_bytes_per_launch"),
                 "wavefronts_per_ray_step": wf, "roof_g_ray_steps_per_s": peak / wf / 1e9, "sm_mhz": mhz, "num_sms": sms,
-                "source": "wavefronts per ray-step and DRAM bytes per launch from profiles/r02_c4_wave_ncu.json (ncu --set full of this kernel on this workload); "
+                "source": "wavefronts per ray-step and DRAM bytes per launch from profiles/r02_c4_wave_ncu.json (ncu capture of this kernel -- the all-clear wavefront variant, 4 CTAs per SM -- on this workload, metric list of tools/ncu_summary.py); "
                           "rate from this run, clock = the SM clock nvidia-smi reports now"}
     except Exception as e:
         return {"error": "%s: %s" % (type(e).__name__, e)}

@@ -1192,6 +1192,12 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
 }
 
 // ---- wavefront mode (vrt_wave.cuh): ONE cooperative launch does bucket passes + marching, round by round -------------------
+// rays per brick from which the all-clear wavefront kernel runs 4 instead of 3 CTAs per SM (VRT_WAVE_DENSE_RAYS_PER_BRICK overrides: tuning)
+static int64_t wave_dense_threshold()
+{
+    static const int64_t v = [] { const char *e = std::getenv("VRT_WAVE_DENSE_RAYS_PER_BRICK"); return e ? (int64_t)std::atoll(e) : (int64_t)1536; }();
+    return v;
+}
 template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR = false>
 static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
 {
@@ -1204,6 +1210,10 @@ static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t 
     if (e != cudaSuccess) return e;
     const int cap = (int)s->opt_wave_ctas.load();
     if (cap > 0 && cap < per_sm) per_sm = cap;
+    // The rays in flight (resident threads) spread over [threads / rays per brick] bricks, whose boxes L2 has to hold: a fourth CTA per SM
+    // pays when bricks are dense (config 4, 8 M rays over 4096 bricks = 2048 rays per brick: 95.5 -> 101.2 G ray-steps/s) and costs when
+    // they are sparse (1 M rays, 256 per brick: 59.6 -> 52.8; profiles/r02_c4_sweep_allclear.log)
+    else if (cap == 0 && per_sm > 3 && wp.m.n / std::max<uint64_t>(wp.K, 1) < (uint64_t)wave_dense_threshold()) per_sm = 3;
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)(per_sm * s->num_sms);          // cooperative: every CTA must be resident
     void *args[] = {(void *)&wp};

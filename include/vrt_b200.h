@@ -108,11 +108,12 @@ enum {
     VRT_OPT_WAVE_MARGIN   = 9,  /* voxels a ray may travel beyond its brick before it is re-bucketed (default 8) */
     VRT_OPT_WAVE_CHECK    = 10, /* marching steps between two refill polls of a warp (default 16) */
     VRT_OPT_WAVE_TAIL_PERMILLE = 11, /* when at most this share of the batch is still alive, the rest is marched without bricks (default 20) */
-    VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = occupancy limit) */
+    VRT_OPT_WAVE_CTAS_PER_SM = 12, /* cap on resident CTAs per SM of the wavefront kernel (0 = the library's choice: the occupancy limit, one less for sparse batches of the all-clear variant) */
     VRT_OPT_WAVE_REFILL   = 14, /* a warp takes new rays from the brick-sorted list when at least this many lanes are idle (default 8) */
     VRT_OPT_ALL_CLEAR_KERNEL = 18, /* 1 (default): a scene in which NO voxel can make a sample opaque (channel 3 carries the sign bit everywhere; counted once at
                                    scene creation, VRT_INFO_ALL_CLEAR) is marched by a variant of the default kernel without the per-cell clear test (KVER 11,
-                                   chosen implicitly like 9: same bits); 0: always the kernel with the test */
+                                   chosen implicitly like 9: same bits), and the wavefront marcher runs its variant that keeps no channel 3 in the cell
+                                   cache (64 registers: 4 instead of 3 resident CTAs per SM for dense batches); 0: always the kernels with the test */
     VRT_INFO_ALL_CLEAR    = 103, /* read-only: 1 if no voxel of the scene has a non-negative channel 3 */
     VRT_INFO_WAVE_ROUNDS  = 102, /* read-only: rounds the last wavefront launch on this scene took (synchronises) */
     VRT_OPT_REGION_ROUNDS = 7,  /* accepted for compatibility, unused (the wavefront marcher runs as many rounds as the batch needs) */

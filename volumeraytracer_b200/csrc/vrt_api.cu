@@ -1195,7 +1195,7 @@ static cudaError_t launch_vox(const vrt_scene *s, const MarchParams &p, bool dir
 // rays per brick from which the all-clear wavefront kernel runs 4 instead of 3 CTAs per SM (VRT_WAVE_DENSE_RAYS_PER_BRICK overrides: tuning)
 static int64_t wave_dense_threshold()
 {
-    static const int64_t v = [] { const char *e = std::getenv("VRT_WAVE_DENSE_RAYS_PER_BRICK"); return e ? (int64_t)std::atoll(e) : (int64_t)1536; }();
+    static const int64_t v = [] { const char *e = std::getenv("VRT_WAVE_DENSE_RAYS_PER_BRICK"); return e ? (int64_t)std::atoll(e) : (int64_t)768; }();
     return v;
 }
 template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR = false>

@@ -114,8 +114,6 @@ enum {
                                    scene creation, VRT_INFO_ALL_CLEAR) is marched by a variant of the default kernel without the per-cell clear test (KVER 11,
                                    chosen implicitly like 9: same bits), and the wavefront marcher runs its variant that keeps no channel 3 in the cell
                                    cache (64 registers: 4 instead of 3 resident CTAs per SM for dense batches); 0: always the kernels with the test */
-    VRT_OPT_WAVE_REUSE    = 19, /* wavefront marcher, all-clear scenes: a move to a face-neighbour cell keeps the 4 shared corners in registers and loads only
-                                   the 4 new ones (csrc/vrt_wave.cuh).  0 off, 1 on, 2 on in the build for 3 CTAs per SM; same bits */
     VRT_INFO_ALL_CLEAR    = 103, /* read-only: 1 if no voxel of the scene has a non-negative channel 3 */
     VRT_INFO_WAVE_ROUNDS  = 102, /* read-only: rounds the last wavefront launch on this scene took (synchronises) */
     VRT_OPT_REGION_ROUNDS = 7,  /* accepted for compatibility, unused (the wavefront marcher runs as many rounds as the batch needs) */

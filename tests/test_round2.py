@@ -440,12 +440,11 @@ def test_wavefront_all_clear_variant_is_bit_identical(vrt, oracle, volk, dirk, k
         d[300:400] *= np.float32(1e25)
     for isc, iters in (([1.0, 1.0, 1.0], 600), ([0.9, 1.3, 1.0], 600), ([1.0, 1.0, 1.0], 7)):
         want = oracle.trace(vol, ob, pos, d, isc, iters, round_mode=oracle.ROUND_DEVICE)
-        for k, margin, check, allclear, reuse in ((3, 2, 16, 1, 0), (4, 0, 5, 1, 1), (5, 8, 16, 1, 1), (3, 2, 16, 1, 2), (4, 1, 1, 1, 2), (3, 2, 16, 0, 1), (-1, 2, 16, 1, 1)):
+        for k, margin, check, allclear in ((3, 2, 16, 1), (4, 0, 5, 1), (5, 8, 16, 1), (3, 2, 16, 0), (-1, 2, 16, 1)):
             t.set_option(vrt.VRT_OPT_WAVE_LOG2, k); t.set_option(vrt.VRT_OPT_WAVE_MARGIN, margin)
             t.set_option(vrt.VRT_OPT_WAVE_CHECK, check); t.set_option(vrt.VRT_OPT_ALL_CLEAR_KERNEL, allclear)
-            t.set_option(vrt.VRT_OPT_WAVE_REUSE, reuse)             # face-neighbour moves keep the 4 shared corners in registers
             got = t.trace_rays_cu(pos, d, isc, 0, iters)
-            _assert_same(got, want[:4], "all-clear wavefront k=%d margin=%d check=%d allclear=%d reuse=%d isc=%s %s/%s" % (k, margin, check, allclear, reuse, isc, volk, dirk))
+            _assert_same(got, want[:4], "all-clear wavefront k=%d margin=%d check=%d allclear=%d isc=%s %s/%s" % (k, margin, check, allclear, isc, volk, dirk))
             if k > 0:
                 assert t.get_option(vrt.VRT_INFO_WAVE_ROUNDS) >= 1
         if iters == 7:

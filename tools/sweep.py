@@ -29,9 +29,9 @@ def timed(fn, reps=2):
 
 
 KV_OPTS = {"wave": "VRT_OPT_WAVE_LOG2", "margin": "VRT_OPT_WAVE_MARGIN", "check": "VRT_OPT_WAVE_CHECK", "tail": "VRT_OPT_WAVE_TAIL_PERMILLE",
-           "wctas": "VRT_OPT_WAVE_CTAS_PER_SM", "wrefill": "VRT_OPT_WAVE_REFILL", "allclear": "VRT_OPT_ALL_CLEAR_KERNEL", "reuse": "VRT_OPT_WAVE_REUSE", "region": "VRT_OPT_REGION_LOG2", "rounds": "VRT_OPT_REGION_ROUNDS", "kver": "VRT_OPT_KERNEL",
+           "wctas": "VRT_OPT_WAVE_CTAS_PER_SM", "wrefill": "VRT_OPT_WAVE_REFILL", "allclear": "VRT_OPT_ALL_CLEAR_KERNEL", "region": "VRT_OPT_REGION_LOG2", "rounds": "VRT_OPT_REGION_ROUNDS", "kver": "VRT_OPT_KERNEL",
            "block": "VRT_OPT_BLOCK_THREADS", "refill": "VRT_OPT_REFILL", "poll": "VRT_OPT_STEPS_PER_POLL", "ctas": "VRT_OPT_MAX_CTAS_PER_SM"}
-KV_DEFAULTS = {"wave": -1, "margin": 8, "check": 16, "tail": 20, "wctas": 0, "wrefill": 8, "allclear": 1, "reuse": 0, "region": 0, "rounds": 12, "kver": 0, "block": 128, "refill": 32, "poll": 128, "ctas": 0}
+KV_DEFAULTS = {"wave": -1, "margin": 8, "check": 16, "tail": 20, "wctas": 0, "wrefill": 8, "allclear": 1, "region": 0, "rounds": 12, "kver": 0, "block": 128, "refill": 32, "poll": 128, "ctas": 0}
 
 
 def run_kv_variants(name, co, tpos, tdir, iterations, variants, live=False):

@@ -21,7 +21,6 @@ VRT_OPT_REGION_LOG2, VRT_OPT_REGION_ROUNDS = 6, 7
 VRT_OPT_WAVE_LOG2, VRT_OPT_WAVE_MARGIN, VRT_OPT_WAVE_CHECK, VRT_OPT_WAVE_TAIL_PERMILLE, VRT_OPT_WAVE_CTAS_PER_SM = 8, 9, 10, 11, 12
 VRT_OPT_WAVE_REFILL = 14
 VRT_OPT_ALL_CLEAR_KERNEL = 18
-VRT_OPT_WAVE_REUSE = 19
 VRT_INFO_ALL_CLEAR = 103
 VRT_INFO_WAVE_ROUNDS = 102
 VRT_INFO_EMPTY_PERMILLE = 100

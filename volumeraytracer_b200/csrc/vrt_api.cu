@@ -111,7 +111,7 @@ struct vrt_scene
     unsigned long long *d_stats = nullptr;   // VRT_OPT_KERNEL 10: kStatSlots block counters (see kStat* in vrt_march.cuh), zeroed when the option is set
     // options
     std::atomic<int64_t> opt_kernel{0}, opt_block{128}, opt_refill{32}, opt_chunk{0}, opt_poll{128}, opt_max_ctas{0}, opt_region{0}, opt_rounds{12};
-    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8}, opt_allclear{1}, opt_wave_reuse{0};
+    std::atomic<int64_t> opt_wave{0}, opt_wave_margin{8}, opt_wave_check{16}, opt_wave_tail{20}, opt_wave_ctas{0}, opt_wave_refill{8}, opt_allclear{1};
 };
 
 static size_t elem_size(int dtype) { return dtype == VRT_I16 ? 2 : 4; }
@@ -706,7 +706,6 @@ int vrt_scene_set_option(vrt_scene *s, int key, int64_t v)
     case VRT_OPT_WAVE_CTAS_PER_SM: if (v < 0 || v > 8) return fail(VRT_ERR_INVALID, "wavefront CTAs per SM must be 0..8"); s->opt_wave_ctas = v; break;
     case VRT_OPT_WAVE_REFILL:    if (v < 1 || v > 32) return fail(VRT_ERR_INVALID, "wavefront refill threshold must be 1..32"); s->opt_wave_refill = v; break;
     case VRT_OPT_ALL_CLEAR_KERNEL: if (v < 0 || v > 1) return fail(VRT_ERR_INVALID, "must be 0 or 1"); s->opt_allclear = v; break;
-    case VRT_OPT_WAVE_REUSE:     if (v < 0 || v > 2) return fail(VRT_ERR_INVALID, "must be 0, 1 or 2"); s->opt_wave_reuse = v; break;
     default: return fail(VRT_ERR_INVALID, "unknown option");
     }
     return VRT_OK;
@@ -732,7 +731,6 @@ int vrt_scene_get_option(const vrt_scene *s, int key, int64_t *v)
     case VRT_OPT_WAVE_CTAS_PER_SM: *v = s->opt_wave_ctas; break;
     case VRT_OPT_WAVE_REFILL: *v = s->opt_wave_refill; break;
     case VRT_OPT_ALL_CLEAR_KERNEL: *v = s->opt_allclear; break;
-    case VRT_OPT_WAVE_REUSE: *v = s->opt_wave_reuse; break;
     case VRT_INFO_ALL_CLEAR: *v = s->all_clear ? 1 : 0; break;
     case VRT_INFO_WAVE_ROUNDS: *v = s->last_wave_rounds_host(); break;
     case VRT_INFO_EMPTY_PERMILLE: *v = (int64_t)(s->flat_fraction * 1000.0 + 0.5); break;
@@ -774,7 +772,7 @@ static int clone_empty(const vrt_scene *src, int device, vrt_scene **out)
     s->opt_region = src->opt_region.load(); s->opt_rounds = src->opt_rounds.load();
     s->opt_wave = src->opt_wave.load(); s->opt_wave_margin = src->opt_wave_margin.load(); s->opt_wave_check = src->opt_wave_check.load();
     s->opt_wave_tail = src->opt_wave_tail.load(); s->opt_wave_ctas = src->opt_wave_ctas.load();
-    s->opt_wave_refill = src->opt_wave_refill.load(); s->opt_allclear = src->opt_allclear.load(); s->opt_wave_reuse = src->opt_wave_reuse.load();
+    s->opt_wave_refill = src->opt_wave_refill.load(); s->opt_allclear = src->opt_allclear.load();
     *out = s;
     return VRT_OK;
 }
@@ -1200,10 +1198,10 @@ static int64_t wave_dense_threshold()
     static const int64_t v = [] { const char *e = std::getenv("VRT_WAVE_DENSE_RAYS_PER_BRICK"); return e ? (int64_t)std::atoll(e) : (int64_t)768; }();
     return v;
 }
-template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR = false, bool REUSE = false, int MINCTAS = WaveBounds<ALLCLEAR>::kMinCtas>
+template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR = false>
 static cudaError_t launch_wave(const vrt_scene *s, WaveParams &wp, cudaStream_t st)
 {
-    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE, ALLCLEAR, REUSE, MINCTAS>;
+    auto kern = march3_wave_kernel<VoxT, DIR_I16, LIVE, ALLCLEAR>;
     static std::atomic<unsigned long long> carved{0};  // per device: next to no shared memory in use, give the unified array to L1
     const unsigned long long bit = 1ull << (s->device & 63);
     if (!(carved.fetch_or(bit) & bit)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -1269,16 +1267,7 @@ static int enqueue_march_wave(const vrt_scene *s, const MarchParams &mp, bool di
         // a scene without any possibly opaque voxel (VRT_INFO_ALL_CLEAR; shipped translucency behaviour): the variant that keeps no channel 3
         // in its cell cache -- 64 registers, 4 resident CTAs per SM instead of 3 (same bits: vrt_wave.cuh)
         const bool allclear = s->all_clear && s->opt_allclear.load() != 0 && !live;
-        const int reuse = allclear ? (int)s->opt_wave_reuse.load() : 0;
-        if (reuse == 1 && s->store == VRT_F32)
-            err = di16 ? launch_wave<float, true, false, true, true>(s, wp, st) : launch_wave<float, false, false, true, true>(s, wp, st);
-        else if (reuse == 1)
-            err = di16 ? launch_wave<int16_t, true, false, true, true>(s, wp, st) : launch_wave<int16_t, false, false, true, true>(s, wp, st);
-        else if (reuse == 2 && s->store == VRT_F32)
-            err = di16 ? launch_wave<float, true, false, true, true, 3>(s, wp, st) : launch_wave<float, false, false, true, true, 3>(s, wp, st);
-        else if (reuse == 2)
-            err = di16 ? launch_wave<int16_t, true, false, true, true, 3>(s, wp, st) : launch_wave<int16_t, false, false, true, true, 3>(s, wp, st);
-        else if (allclear && s->store == VRT_F32)
+        if (allclear && s->store == VRT_F32)
             err = di16 ? launch_wave<float, true, false, true>(s, wp, st) : launch_wave<float, false, false, true>(s, wp, st);
         else if (allclear)
             err = di16 ? launch_wave<int16_t, true, false, true>(s, wp, st) : launch_wave<int16_t, false, false, true>(s, wp, st);

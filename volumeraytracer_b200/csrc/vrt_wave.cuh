@@ -139,27 +139,8 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t &total, uint
 // registers, 24 instead of 30 instructions per sample; same bits, see trilerp_z) and the kernel fits 4 resident CTAs per SM.
 template <bool ALLCLEAR> struct WaveBounds { static constexpr int kMinCtas = ALLCLEAR ? VRT_WAVE_MINCTAS_ALLCLEAR : VRT_WAVE_MINCTAS; };
 
-//
-// REUSE (all-clear variant only): a step moves a ray by about a quarter of a voxel, so nearly every cell change is a move to a FACE
-// neighbour, which shares 4 of its 8 corners with the cell in the cache.  On incoherent rays every lane of a corner load is a
-// data-pipe wavefront of its own (the roof of this kernel), so those 4 corners are taken from the registers they are in (12-16 register
-// moves, one straight-line case per direction) and only the 4 new ones are loaded: 4 instead of 8 wavefronts per ray and cell change.
-// Anything else (first cell of a round, an edge/corner move, a jump) reloads all 8.  Pure data movement: the cache holds the same
-// values either way.
-template <typename VoxT>
-__device__ __forceinline__ void wave_set_row(CornersZ &c, int r, const float4 &v0, const float4 &v1, uint32_t zero)
-{
-    c.lo[r][0] = pack2(v0.x, v0.y);
-    c.lo[r][1] = pack2(v1.x, v1.y);
-    c.zp[r] = pack2(v0.z, __uint_as_float(__float_as_uint(v1.z) | (sizeof(VoxT) == 4 ? zero : 0u)));     // see corners_to_z
-}
-__device__ __forceinline__ void wave_copy_row(CornersZ &c, int dst, int src)
-{
-    c.lo[dst][0] = c.lo[src][0]; c.lo[dst][1] = c.lo[src][1]; c.zp[dst] = c.zp[src];
-}
-
-template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR, bool REUSE = false, int MINCTAS = WaveBounds<ALLCLEAR>::kMinCtas>
-__global__ void __launch_bounds__(kWaveThreads, MINCTAS) march3_wave_kernel(const WaveParams p)
+template <typename VoxT, bool DIR_I16, bool LIVE, bool ALLCLEAR>
+__global__ void __launch_bounds__(kWaveThreads, (WaveBounds<ALLCLEAR>::kMinCtas)) march3_wave_kernel(const WaveParams p)
 {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const MarchParams &m = p.m;
@@ -267,7 +248,6 @@ __global__ void __launch_bounds__(kWaveThreads, MINCTAS) march3_wave_kernel(cons
             bool have = false, exhausted = false;                                    // exhausted: warp-uniform, the list has been handed out
             CornersP q;             // cell cache (generic)
             CornersZ cz;            // cell cache without channel 3 (ALLCLEAR)
-            uint32_t ckey = 0xFFFFFFFFu, cpz = 0xFFFF0000u;   // REUSE: the cell in the cache, (x>>16 | y>>16 << 16) and a position with its z>>16 (no cell has these values: nvox < 2^32)
             for (;;)
             {
                 if (!exhausted)
@@ -291,7 +271,6 @@ __global__ void __launch_bounds__(kWaveThreads, MINCTAS) march3_wave_kernel(cons
                                 it = p.st_it[ray];
                                 if (LIVE) brightness = p.st_light[ray];
                                 moved = 0xFFFFFFFFu;
-                                ckey = 0xFFFFFFFFu; cpz = 0xFFFF0000u;
                                 if (tail) { lo_x = lo_y = lo_z = 0; sp_x = m.limx16; sp_y = m.limy16; sp_z = m.limz16; }
                                 else
                                 {
@@ -329,81 +308,11 @@ __global__ void __launch_bounds__(kWaveThreads, MINCTAS) march3_wave_kernel(cons
                         --it;
                         if (moved >= 0x10000u)
                         {
-                            const uint32_t ix = px >> 16, iy = py >> 16, iz = pz >> 16;
-                            const uint32_t cell = (ix * m.by + iy) * m.bz + iz;                              // cu:113
+                            const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
                             VRT_CHK(cell < m.nvox);
                             if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
-                            if (ALLCLEAR && REUSE)
-                            {
-                                // the move since the cell in the cache was loaded, per axis, plus one: 0, 1, 2 for -1, 0, +1
-                                const uint32_t ex = ix - (ckey & 0xFFFFu) + 1u, ey = iy - (ckey >> 16) + 1u, ez = iz - (cpz >> 16) + 1u;
-                                const uint32_t code = (ex | ey | ez) < 4u ? ex + 4u * ey + 16u * ez : 0u;
-                                ckey = __byte_perm(px, py, 0x7632); cpz = pz;
-                                VRT_CHK((unsigned long long)cell * Vox<VoxT>::kBytes3 + m.row3 + 2ull * Vox<VoxT>::kBytes3 <= m.vol_bytes);
-                                constexpr int VB = Vox<VoxT>::kBytes3;
-                                const char *r0 = (const char *)m.volume + (size_t)cell * VB;
-                                if (code == 22u)          // +x: rows (x+1, .) become rows (x, .)
-                                {
-                                    wave_copy_row(cz, 0, 2); wave_copy_row(cz, 1, 3);
-                                    const char *r2 = r0 + m.row2, *r3 = r0 + m.row3;
-                                    const float4 a0 = load_voxel_z<VoxT>(r2), a1 = load_voxel_z<VoxT>(r2 + VB), b0 = load_voxel_z<VoxT>(r3), b1 = load_voxel_z<VoxT>(r3 + VB);
-                                    wave_set_row<VoxT>(cz, 2, a0, a1, m.zero); wave_set_row<VoxT>(cz, 3, b0, b1, m.zero);
-                                }
-                                else if (code == 20u)     // -x
-                                {
-                                    wave_copy_row(cz, 2, 0); wave_copy_row(cz, 3, 1);
-                                    const char *r1 = r0 + m.row1;
-                                    const float4 a0 = load_voxel_z<VoxT>(r0), a1 = load_voxel_z<VoxT>(r0 + VB), b0 = load_voxel_z<VoxT>(r1), b1 = load_voxel_z<VoxT>(r1 + VB);
-                                    wave_set_row<VoxT>(cz, 0, a0, a1, m.zero); wave_set_row<VoxT>(cz, 1, b0, b1, m.zero);
-                                }
-                                else if (code == 25u)     // +y: rows (., y+1) become rows (., y)
-                                {
-                                    wave_copy_row(cz, 0, 1); wave_copy_row(cz, 2, 3);
-                                    const char *r1 = r0 + m.row1, *r3 = r0 + m.row3;
-                                    const float4 a0 = load_voxel_z<VoxT>(r1), a1 = load_voxel_z<VoxT>(r1 + VB), b0 = load_voxel_z<VoxT>(r3), b1 = load_voxel_z<VoxT>(r3 + VB);
-                                    wave_set_row<VoxT>(cz, 1, a0, a1, m.zero); wave_set_row<VoxT>(cz, 3, b0, b1, m.zero);
-                                }
-                                else if (code == 17u)     // -y
-                                {
-                                    wave_copy_row(cz, 1, 0); wave_copy_row(cz, 3, 2);
-                                    const char *r2 = r0 + m.row2;
-                                    const float4 a0 = load_voxel_z<VoxT>(r0), a1 = load_voxel_z<VoxT>(r0 + VB), b0 = load_voxel_z<VoxT>(r2), b1 = load_voxel_z<VoxT>(r2 + VB);
-                                    wave_set_row<VoxT>(cz, 0, a0, a1, m.zero); wave_set_row<VoxT>(cz, 2, b0, b1, m.zero);
-                                }
-                                else if (code == 37u)     // +z: the (., ., z+1) corners become the (., ., z) corners
-                                {
-                                    const char *r1 = r0 + m.row1, *r2 = r0 + m.row2, *r3 = r0 + m.row3;
-                                    const float4 v0 = load_voxel_z<VoxT>(r0 + VB), v1 = load_voxel_z<VoxT>(r1 + VB), v2 = load_voxel_z<VoxT>(r2 + VB), v3 = load_voxel_z<VoxT>(r3 + VB);
-                                    const float4 v[4] = {v0, v1, v2, v3};
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r)
-                                    {
-                                        float zl, zh;
-                                        unpack2(cz.zp[r], zl, zh);
-                                        cz.lo[r][0] = cz.lo[r][1];
-                                        cz.lo[r][1] = pack2(v[r].x, v[r].y);
-                                        cz.zp[r] = pack2(zh, v[r].z);
-                                    }
-                                }
-                                else if (code == 5u)      // -z
-                                {
-                                    const char *r1 = r0 + m.row1, *r2 = r0 + m.row2, *r3 = r0 + m.row3;
-                                    const float4 v0 = load_voxel_z<VoxT>(r0), v1 = load_voxel_z<VoxT>(r1), v2 = load_voxel_z<VoxT>(r2), v3 = load_voxel_z<VoxT>(r3);
-                                    const float4 v[4] = {v0, v1, v2, v3};
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r)
-                                    {
-                                        float zl, zh;
-                                        unpack2(cz.zp[r], zl, zh);
-                                        cz.lo[r][1] = cz.lo[r][0];
-                                        cz.lo[r][0] = pack2(v[r].x, v[r].y);
-                                        cz.zp[r] = pack2(v[r].z, zl);
-                                    }
-                                }
-                                else load_corners_z<VoxT>(cz, m, cell);
-                            }
-                            else if (ALLCLEAR) load_corners_z<VoxT>(cz, m, cell);
-                            else               load_corners<VoxT>(q, m, cell);
+                            if (ALLCLEAR) load_corners_z<VoxT>(cz, m, cell);
+                            else          load_corners<VoxT>(q, m, cell);
                         }
                         if (LIVE)                                                                            // cu:337-341
                         {

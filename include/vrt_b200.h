@@ -190,7 +190,8 @@ VRT_API int vrt_scene_replicate(const vrt_scene *src, int n, const int *devices,
  * vrt_comm_create, which also runs a 4-byte broadcast so that NCCL's lazy connection set-up is not billed to the first scene.
  * vrt_scene_broadcast replicates root's scene: on root `src` is the scene and *out == src; elsewhere src is ignored and *out
  * is a new scene on the communicator's device.  The staged buffers are broadcast in place (no export copy).  *seconds (may be
- * NULL) = device time of the payload broadcasts (CUDA events on the communicator's stream). */
+ * NULL) = device time of the payload broadcasts (CUDA events on the communicator's stream); the ranks meet in a 4-byte all-reduce
+ * after the receivers have allocated their replica, so that time holds the transfer and not the receivers' cudaMalloc. */
 typedef struct vrt_comm vrt_comm;
 VRT_API int vrt_comm_unique_id(void *id_128_bytes);
 VRT_API int vrt_comm_create(vrt_comm **out, int device, int rank, int world, const void *id_128_bytes);

@@ -830,6 +830,7 @@ struct NcclApi
     int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;    // optional: the rendezvous of vrt_scene_broadcast
     const char *(*GetErrorString)(int) = nullptr;
     int (*GetVersion)(int *) = nullptr;
     bool ok = false;
@@ -851,6 +852,7 @@ NcclApi &nccl()
         api.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
         api.CommDestroy = (int (*)(void *))dlsym(api.handle, "ncclCommDestroy");
         api.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
+        api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
         api.GetErrorString = (const char *(*)(int))dlsym(api.handle, "ncclGetErrorString");
         api.GetVersion = (int (*)(int *))dlsym(api.handle, "ncclGetVersion");
         api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.GetErrorString;
@@ -977,7 +979,8 @@ int vrt_comm_create(vrt_comm **out, int device, int rank, int world, const void 
     int r = nccl().CommInitRank(&c->comm, world, u, rank);
     if (r != 0) { delete c; return fail(VRT_ERR_CUDA, std::string("NCCL: ") + nccl().GetErrorString(r) + " (ncclCommInitRank)"); }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    e = e == cudaSuccess ? cudaMalloc((void **)&c->d_hdr, 256) : e;
+    e = e == cudaSuccess ? cudaMalloc((void **)&c->d_hdr, 512) : e;      // 256-byte scene header + a word for the rendezvous
+    e = e == cudaSuccess ? cudaMemset(c->d_hdr, 0, 512) : e;
     // warm-up: NCCL connects its channels lazily on the first collective; do that here, not inside the first scene broadcast
     void *warm = nullptr;
     e = e == cudaSuccess ? cudaMalloc(&warm, 8u << 20) : e;
@@ -985,6 +988,7 @@ int vrt_comm_create(vrt_comm **out, int device, int rank, int world, const void 
     {
         r = nccl().Broadcast(c->d_hdr, c->d_hdr, 4, 0, 0, c->comm, c->stream);
         if (r == 0) r = nccl().Broadcast(warm, warm, 8u << 20, 0, 0, c->comm, c->stream);
+        if (r == 0 && nccl().AllReduce) r = nccl().AllReduce(c->d_hdr + 256, c->d_hdr + 256, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->comm, c->stream);
         e = cudaStreamSynchronize(c->stream);
     }
     if (warm) cudaFree(warm);
@@ -1059,12 +1063,22 @@ int vrt_scene_broadcast(vrt_comm *c, int root, vrt_scene *src, vrt_scene **out, 
         proto.d_translucency = nullptr; proto.d_ior = nullptr;
         if (rc) { const std::string msg = g_last_error; vrt_scene_destroy(s); return fail(rc, msg); }
     }
-    cudaEvent_t a = nullptr, b = nullptr;
-    cudaError_t e = cudaEventCreate(&a);
-    e = e == cudaSuccess ? cudaEventCreate(&b) : e;
-    e = e == cudaSuccess ? cudaEventRecord(a, c->stream) : e;
+    // Rendezvous: the receiving ranks have just allocated their replica (a cudaMalloc of the whole scene takes tens of milliseconds).  Without
+    // it the root's broadcast kernel starts at once and waits for them on the device, so the root's `seconds` -- and the maximum over the ranks
+    // -- would be the receivers' allocation time plus the transfer (seen as 181 instead of ~600 GB/s on 2 GPUs).  A 4-byte all-reduce: every
+    // rank has to arrive.
     int r = 0;
-    if (e == cudaSuccess)
+    cudaError_t e = cudaSuccess;
+    if (nccl().AllReduce)
+    {
+        r = nccl().AllReduce(c->d_hdr + 256, c->d_hdr + 256, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->comm, c->stream);
+        e = r == 0 ? cudaStreamSynchronize(c->stream) : e;
+    }
+    cudaEvent_t a = nullptr, b = nullptr;
+    e = e == cudaSuccess && r == 0 ? cudaEventCreate(&a) : e;
+    e = e == cudaSuccess && r == 0 ? cudaEventCreate(&b) : e;
+    e = e == cudaSuccess && r == 0 ? cudaEventRecord(a, c->stream) : e;
+    if (e == cudaSuccess && r == 0)
     {
         r = nccl().Broadcast(s->d_volume, s->d_volume, (size_t)storage_bytes(s), 0, root, c->comm, c->stream);       // in place on every rank
         if (r == 0 && h.has_tr) r = nccl().Broadcast(s->d_translucency, s->d_translucency, (size_t)(s->nvox * 4), 0, root, c->comm, c->stream);

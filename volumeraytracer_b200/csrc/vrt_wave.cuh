@@ -310,13 +310,13 @@ __global__ void __launch_bounds__(kWaveThreads, (WaveBounds<ALLCLEAR>::kMinCtas)
                         {
                             const uint32_t cell = ((px >> 16) * m.by + (py >> 16)) * m.bz + (pz >> 16);       // cu:113
                             VRT_CHK(cell < m.nvox);
-                            if (LIVE) cached_tr = ldg_nc_u32(m.translucency + cell);
+                            if (LIVE) cached_tr = 0xFFFFFFFFu - ldg_nc_u32(m.translucency + cell);
                             if (ALLCLEAR) load_corners_z<VoxT>(cz, m, cell);
                             else          load_corners<VoxT>(q, m, cell);
                         }
                         if (LIVE)                                                                            // cu:337-341
                         {
-                            const uint32_t absorb = 0xFFFFFFFFu - cached_tr;
+                            const uint32_t absorb = cached_tr;
                             brightness -= min(brightness, absorb);
                             if (brightness < m.min_brightness) { done = true; it_final = it + 1u; break; }
                         }

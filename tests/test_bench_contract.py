@@ -27,3 +27,21 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_sass_profile_matches_the_shipped_binary():
+    """bench.py's issue roofline multiplies block execution counts by the SASS lengths of the marcher's blocks.  The committed
+    profiles/r02_sass_blocks.json (and the listing next to it) must be the ones of the library that is built from this tree: the tool
+    is re-run on libvrt_b200.so and the opcode-stream hashes compared, so a kernel change without refreshed profiles fails here."""
+    import shutil
+    import pytest
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")):
+        pytest.skip("CUDA binary tools not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_blocks
+    committed = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_blocks.json")))
+    live = sass_blocks.analyse(sass_blocks.disassemble(os.path.join(ROOT, "volumeraytracer_b200", "libvrt_b200.so"), committed["kernel"]))
+    assert live["sass_sha1"] == committed["sass_sha1"], "profiles/r02_sass_blocks.json is stale: re-run tools/sass_blocks.py"
+    assert live["blocks"] == committed["blocks"]
+    # the fast loop of the all-clear kernel: 64 instructions per step, 27 per cell reload (DESIGN.md section 5)
+    assert committed["blocks"]["fast_step"] <= 64 and committed["blocks"]["reload"] <= 27
